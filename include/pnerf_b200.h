@@ -1,0 +1,190 @@
+/* pnerf_b200.h -- C ABI of libpnerf_b200.so: Point-NeRF's per-ray hot path on B200 (sm_100a).
+ *
+ * Drop-in boundary for the reference's only native entry point and for the torch code around it
+ * (reference = SHUzhekiNg/pointnerf2studio; paths relative to /root/reference/pointnerf/):
+ *   CPP = models/neural_points/cuda/query_worldcoords.cpp   CU = .../query_worldcoords.cu
+ *   SU  = nerfstudio/studio_utils.py                        SM = nerfstudio/studio_model.py
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _h (host); nothing here allocates
+ *     or frees device memory, the caller (torch) owns every buffer, inputs are never written;
+ *   - `stream` is a cudaStream_t passed as void*; every launch goes to it, nothing synchronises
+ *     (the reference launches on the legacy default stream and blocks the host five times per call,
+ *     CU:310,382,426);
+ *   - return value: 0 = PNERF_OK, negative = error (never throws; the reference raises nothing and
+ *     checks nothing, CPP:51-53);
+ *   - all floats are fp32, all indices int32, B = 1 (the reference always runs with B = 1).
+ */
+#ifndef PNERF_B200_H
+#define PNERF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNERF_OK 0
+#define PNERF_ERR_ARG (-1)      /* bad size / null pointer / unsupported K, P, kernel size */
+#define PNERF_ERR_CUDA (-2)     /* a CUDA runtime call failed; see pnerf_last_cuda_error() */
+#define PNERF_ERR_WORKSPACE (-3)/* workspace too small */
+#define PNERF_ERR_ARCH (-4)     /* device is not sm_100 */
+
+int pnerf_version(void);
+const char* pnerf_last_cuda_error(void);
+/* 0 when the current device can run the tcgen05 kernels (compute capability 10.x) */
+int pnerf_device_check(void);
+
+/* ---------------------------------------------------------------- grid frame (row H)
+ * Replaces NeuralPoints.get_hyperparameters' two reductions (SU:116): min/max over the N points.
+ * out_minmax: 6 floats (min xyz, max xyz).  The fp64 dim arithmetic of SU:125-126 stays on the host. */
+int pnerf_bbox(const float* xyz, int64_t n, float* out_minmax, void* stream);
+
+/* ---------------------------------------------------------------- grid build (row G1)
+ * Replaces claim_occ / map_coor2occ / fill_occ2pnts (CU:18-162, launched CU:322-365) and the
+ * per-call allocations of CU:314-319,337.  Built once per point-cloud version, not per call.
+ * Deterministic: a voxel keeps its first P points in ascending index; all occupied voxels kept.
+ *   lo_h, sv_h, dim_h : grid origin, scaled voxel size, dims (host, 3 each)  [ranges, scaled_vsize, scaled_vdim]
+ *   query_size_h      : dilation box of the occupancy (CU:342 passes query_size)
+ * outputs
+ *   cell_start [G+1]  : CSR offsets into `recs`, cell id = x*dimy*dimz + y*dimz + z (CU:45)
+ *   recs [n] float4   : (x, y, z, bits(point index | (vz & 7) << 28)) of kept points, sorted by
+ *                       (cell, index); only the first cell_start[G] entries are valid
+ *   occ_bits [ceil(G/32)] : dilated occupancy, bit (id & 31) of word (id >> 5)   [coor_occ]
+ * workspace: at least pnerf_grid_workspace_bytes(n, G) bytes. */
+int64_t pnerf_grid_workspace_bytes(int64_t n, int64_t cells);
+int pnerf_grid_build(const float* xyz, int64_t n, const float* lo_h, const float* sv_h, const int* dim_h,
+                     int P, const int* query_size_h, int* cell_start, float* recs, uint32_t* occ_bits,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+typedef struct {
+    float lo[3];
+    float sv[3];
+    int dim[3];
+    const int* cell_start;
+    const float* recs;
+    const uint32_t* occ_bits;
+} pnerf_grid_view;
+
+/* ---------------------------------------------------------------- sample selection (rows G0, G2)
+ * Replaces mask_raypos, the torch max/sum/cumsum/masked_select chain and get_shadingloc
+ * (CU:165-214, 368-402).  One of three position sources:
+ *   raypos != NULL              : explicit coarse positions (R,D,3)  -- the reference's own input
+ *   t_vals != NULL, t_stride=0  : pos = origin + dir * t_vals[j]  (one t table for all rays)
+ *   t_vals != NULL, t_stride=D  : per-ray t table (R,D)
+ * (mul then add, separately rounded, as torch evaluates RM:330).
+ * outputs, not compacted over rays:
+ *   sample_loc (R,SR,3) zero where empty; sample_cnt (R) = min(#hits, SR); 0 <=> ray not in R'. */
+int pnerf_sample_select(const pnerf_grid_view* grid_h, const float* raypos, const float* origin_h,
+                        const float* dirs, const float* t_vals, int t_stride, int R, int D, int SR,
+                        float* sample_loc, int* sample_cnt, void* stream);
+
+/* ---------------------------------------------------------------- neighbour query (row Q)
+ * Replaces query_neigh_along_ray_layered (CU:217-302): layer-truncated, bucket-capped,
+ * radius-limited K nearest.  K <= 32; layers = (kernel_size0+1)/2 <= 3.  Tie-break rule: candidates
+ * are visited in (layer, ux, uy, uz, point index) order, the K kept are the K smallest by
+ * (d2, visit order) and are emitted in that order; d2 = fma(dz,dz,fma(dy,dy,dx*dx)).
+ * outputs: sample_pidx (R,SR,K) with -1 padding (every slot is written);
+ *          sample_valid (R*SR) uint8: slot has >= 1 neighbour;
+ *          stats (optional, 2 x uint64): voxel-table entries visited, candidate points examined. */
+int pnerf_query(const pnerf_grid_view* grid_h, const float* sample_loc, const int* sample_cnt, int R, int SR,
+                int K, int kernel_size0, float radius, int* sample_pidx, uint8_t* sample_valid,
+                unsigned long long* stats, void* stream);
+
+/* Ray compaction of the reference's return value (CU:425-432): ray_mask (R) int8 and, when the
+ * caller wants the reference's compact (R'',SR,.) tensors, an index list of the surviving rays.
+ *   ray_index [R] : ids of rays with >= 1 neighbour, ascending;  n_rays [1] : R''. */
+int pnerf_ray_compact(const uint8_t* sample_valid, int R, int SR, int8_t* ray_mask, int* ray_index,
+                      int* n_rays, void* workspace, int64_t workspace_bytes, void* stream);
+int pnerf_gather_rays(const int* ray_index, int n_rays, int SR, int K, const int* sample_pidx,
+                      const float* sample_loc, int* out_pidx, float* out_loc, void* stream);
+
+/* Compact list of valid samples (ascending slot id r*SR+s): sample_ids [R*SR], n_samples [1]. */
+int pnerf_sample_compact(const uint8_t* sample_valid, int64_t n_slots, int* sample_ids, int* n_samples,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+int64_t pnerf_scan_workspace_bytes(int64_t n);
+
+/* ---------------------------------------------------------------- field networks (rows P, GA, W, E, M1, A, M2)
+ * Replaces NeuralPoints.forward's gather (SU:190-209) and PointNerf.get_outputs' field math
+ * (SM:270-366): perspective coords, dists6, inverse-distance weights, positional encodings,
+ * mlp_base, mlp_head, density head, K-aggregation, mlp_color, rgb head. */
+typedef struct {
+    const float* xyz;     /* (N,3)  points_xyz      */
+    const float* embed;   /* (N,32) points_embeding */
+    const float* color;   /* (N,3)  points_color    */
+    const float* dir;     /* (N,3)  points_dir      */
+    const float* conf;    /* (N,1)  points_conf     */
+    float Rw2c[9];        /* points_Rw2c, row major (host copy) */
+    int64_t n;
+} pnerf_points;
+
+typedef struct {
+    float origin[3];      /* ray_bundle.origins[0]             (SU:152) */
+    float R_c2w[9];       /* metadata["camrotc2w"], row major  (SU:148-151) */
+} pnerf_camera;
+
+typedef struct {          /* fp32 weights, torch nn.Linear layout (out,in) row major */
+    const float *w1, *b1; /* mlp_base.layers.0  256x284  [aggregator.block1.0]       */
+    const float *w2, *b2; /* mlp_base.layers.1  256x256  [aggregator.block1.2]       */
+    const float *w3, *b3; /* mlp_head.layers.0  256x263  [aggregator.block3.0]       */
+    const float *w4, *b4; /* mlp_head.layers.1  256x256  [aggregator.block3.2]       */
+    const float *wa, *ba; /* field_output_density.net 1x256 [aggregator.alpha_branch.0] */
+    const float *wc1, *bc1; /* mlp_color.layers.0 128x280 [aggregator.color_branch.0] */
+    const float *wc2, *bc2; /* mlp_color.layers.1 128x128 [aggregator.color_branch.2] */
+    const float *wc3, *bc3; /* mlp_color.layers.2 128x128 [aggregator.color_branch.4] */
+    const float *wc4, *bc4; /* field_output_color.net 3x128 [aggregator.color_branch.6] */
+} pnerf_mlp;
+
+typedef struct {
+    float lrelu_slope;    /* 0.1 plugin (SM:197), 0.01 original flow (PA:286 default slope)      */
+    int density_softplus; /* 0: ReLU (SM:221);  1: Softplus(raw-1) (PA:260-265)                   */
+    int weight_conf;      /* 0: plugin (SM:318); 1: weight * clamp(conf,1e-4,1) (PA:822-826)      */
+    int bg_mode;          /* 0: C += bg*(1-sum w) (SM:387-390); 1: C += bg*T_end (RM:529-532)     */
+    int eval_clamp;       /* 1: nan_to_num + clamp [0,1] (nerfstudio RGBRenderer in eval)         */
+    float bg[3];
+    float vsize_z;        /* config.vsize[2], unscaled (SM:369-374)                               */
+} pnerf_mode;
+
+/* fp32 SIMT implementation (exact-parity path).  Row = (valid sample, neighbour slot), M = S*K rows
+ * incl. masked slots (zero weight).  Saves every activation for the backward pass.
+ * Workspace layout is private; query its size with pnerf_field_f32_workspace_bytes(S, K). */
+int64_t pnerf_field_f32_workspace_bytes(int64_t n_samples, int K);
+int pnerf_field_forward_f32(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h,
+                            const pnerf_mode* mode_h, const float* dirs, const float* sample_loc,
+                            const int* sample_pidx, const int* sample_ids, int n_samples, int SR, int K,
+                            float* sigma /* (R*SR) by slot, 0 elsewhere: caller zero-fills */,
+                            float* rgb /* (R*SR,3) by slot */, void* workspace, int64_t workspace_bytes,
+                            void* stream);
+typedef struct {
+    float *w1, *b1, *w2, *b2, *w3, *b3, *w4, *b4, *wa, *ba, *wc1, *bc1, *wc2, *bc2, *wc3, *bc3, *wc4, *bc4;
+} pnerf_mlp_grad;
+/* Backward of the above: consumes d sigma / d rgb (by slot), accumulates (+=) into the point
+ * gradients (N,32),(N,3),(N,3),(N,1) (may be NULL) and the MLP gradients. */
+int pnerf_field_backward_f32(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h,
+                             const pnerf_mode* mode_h, const float* dirs, const float* sample_loc,
+                             const int* sample_pidx, const int* sample_ids, int n_samples, int SR, int K,
+                             const float* d_sigma, const float* d_rgb, float* g_embed, float* g_color,
+                             float* g_dir, float* g_conf, const pnerf_mlp_grad* g_mlp_h, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- step length + compositing (rows D, C, F)
+ * Replaces SM:368-390 (+ nerfstudio RGBRenderer) and fill_invalid SM:491-504; original-flow twin
+ * NPV:271-279 + ray_march RM:495-541.  One warp per ray, all R rays (missed rays -> bg).
+ *   out_rgb (R,3);  out_weights (R,SR) optional blend weights;  out_T_end (R) optional. */
+int pnerf_composite_forward(const pnerf_camera* cam_h, const pnerf_mode* mode_h, const float* sample_loc,
+                            const uint8_t* sample_valid, const float* sigma, const float* rgb, int R, int SR,
+                            float* out_rgb, float* out_weights, float* out_T_end, void* stream);
+/* d_out (R,3) -> d_sigma (R*SR), d_rgb (R*SR,3), every slot written (0 where invalid). */
+int pnerf_composite_backward(const pnerf_camera* cam_h, const pnerf_mode* mode_h, const float* sample_loc,
+                             const uint8_t* sample_valid, const float* sigma, const float* rgb,
+                             const float* d_out, int R, int SR, float* d_sigma, float* d_rgb, void* stream);
+
+/* Confidence ("zero-one") loss term of SM:288-292,427-429 over ALL R''*SR*K slots (invalid slots
+ * read point 0, SU:194): adds the value to loss_out[0] and its gradient to g_conf (N). */
+int pnerf_conf_loss(const float* conf, const int* sample_pidx, const int8_t* ray_mask, int R, int SR, int K,
+                    float eps, float weight, const int* n_rays /* device R'' */, float* loss_out,
+                    float* g_conf, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

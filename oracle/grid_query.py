@@ -225,7 +225,7 @@ def compact_rays(sample_pidx, sample_loc, ray_hit):
     """Drop rays without any neighbour (CU:425-432): returns compact pidx/loc of the R''
     surviving rays and ray_mask (R,) int8."""
     R = len(ray_hit)
-    has = (sample_pidx >= 0).reshape(R, -1).any(axis=1) & ray_hit
+    has = (sample_pidx >= 0).any(axis=(1, 2)) & ray_hit
     return sample_pidx[has], sample_loc[has], has.astype(np.int8)
 
 

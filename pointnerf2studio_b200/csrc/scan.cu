@@ -1,0 +1,221 @@
+// Exclusive int32 scan (multi-level reduce / scan / add) and the stream compactions built on it.
+// Used by the grid build (cell offsets) and by the ray / sample compaction of the per-call path.
+#include "pnerf_common.cuh"
+
+namespace pnerf {
+
+thread_local char g_last_error[256] = {0};
+
+int set_cuda_error(cudaError_t e, const char* where) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s", where, cudaGetErrorString(e));
+    cudaGetLastError();
+    return PNERF_ERR_CUDA;
+}
+
+namespace {
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;  // 4096
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+    __shared__ int warp_sums[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < kScanThreads / 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    int base = warp > 0 ? warp_sums[warp - 1] : 0;
+    *total = warp_sums[kScanThreads / 32 - 1];
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads) tile_sums_kernel(const int* __restrict__ in, int64_t n,
+                                                                  int* __restrict__ sums) {
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        int64_t j = base + i;
+        if (j < n) s += in[j];
+    }
+    int total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// out[i] = offsets[tile] + exclusive prefix inside the tile.  `offsets` may be null (single tile).
+__global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(const int* in, int* out, int64_t n,
+                                                                  const int* __restrict__ offsets, int write_total) {
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        int64_t j = base + i;
+        v[i] = j < n ? in[j] : 0;
+        s += v[i];
+    }
+    int total;
+    int pre = block_exclusive_scan(s, &total) + (offsets ? offsets[blockIdx.x] : 0);
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        int64_t j = base + i;
+        if (j < n) out[j] = pre;
+        pre += v[i];
+    }
+    if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0)
+        out[n] = (offsets ? offsets[blockIdx.x] : 0) + total;
+}
+}  // namespace
+
+int64_t scan_workspace_bytes(int64_t n) {
+    int64_t bytes = 0;
+    while (n > kScanTile) {
+        n = (n + kScanTile - 1) / kScanTile;
+        bytes += align_up(n * 4, 256);
+    }
+    return bytes + 256;
+}
+
+int exclusive_scan_i32(const int* in, int* out, int64_t n, bool with_total, void* ws, int64_t ws_bytes,
+                       cudaStream_t st) {
+    if (n < 0) return PNERF_ERR_ARG;
+    if (n == 0) {
+        if (with_total) PNERF_CUDA(cudaMemsetAsync(out, 0, 4, st));
+        return PNERF_OK;
+    }
+    if (ws_bytes < scan_workspace_bytes(n)) return PNERF_ERR_WORKSPACE;
+    const int64_t tiles = (n + kScanTile - 1) / kScanTile;
+    if (tiles == 1) {
+        tile_scan_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, nullptr, with_total ? 1 : 0);
+        PNERF_LAUNCH_CHECK();
+        return PNERF_OK;
+    }
+    int* sums = (int*)ws;
+    tile_sums_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, n, sums);
+    PNERF_LAUNCH_CHECK();
+    char* next_ws = (char*)ws + align_up(tiles * 4, 256);
+    int rc = exclusive_scan_i32(sums, sums, tiles, false, next_ws, ws_bytes - align_up(tiles * 4, 256), st);
+    if (rc) return rc;
+    tile_scan_kernel<<<(unsigned)tiles, kScanThreads, 0, st>>>(in, out, n, sums, with_total ? 1 : 0);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void flags_to_i32_kernel(const uint8_t* __restrict__ flags, int64_t n, int* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = flags[i] ? 1 : 0;
+}
+__global__ void scatter_ids_kernel(const uint8_t* __restrict__ flags, const int* __restrict__ pos, int64_t n,
+                                   int* __restrict__ ids, int* __restrict__ count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flags[i]) ids[pos[i]] = (int)i;
+    if (i == 0) *count = pos[n];
+}
+__global__ void ray_flags_kernel(const uint8_t* __restrict__ sample_valid, int R, int SR, int8_t* __restrict__ ray_mask,
+                                 int* __restrict__ flag_i32) {
+    // one warp per ray: ray survives iff any of its SR slots has a neighbour (CU:425-427)
+    int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= R) return;
+    int any = 0;
+    for (int s = lane; s < SR; s += 32) any |= sample_valid[(int64_t)r * SR + s];
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) { ray_mask[r] = any ? 1 : 0; flag_i32[r] = any ? 1 : 0; }
+}
+__global__ void scatter_rays_kernel(const int* __restrict__ flag_pos, const int8_t* __restrict__ ray_mask, int R,
+                                    int* __restrict__ ray_index, int* __restrict__ n_rays) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R && ray_mask[r]) ray_index[flag_pos[r]] = r;
+    if (r == 0) *n_rays = flag_pos[R];
+}
+__global__ void gather_rays_kernel(const int* __restrict__ ray_index, int n_rays, int SR, int K,
+                                   const int* __restrict__ pidx, const float* __restrict__ loc,
+                                   int* __restrict__ out_pidx, float* __restrict__ out_loc) {
+    const int per_ray = SR * (K + 3);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_rays * per_ray) return;
+    int rr = (int)(i / per_ray), e = (int)(i % per_ray);
+    int r = ray_index[rr];
+    if (e < SR * K) out_pidx[(int64_t)rr * SR * K + e] = pidx[(int64_t)r * SR * K + e];
+    else { e -= SR * K; out_loc[(int64_t)rr * SR * 3 + e] = loc[(int64_t)r * SR * 3 + e]; }
+}
+}  // namespace
+}  // namespace pnerf
+
+using namespace pnerf;
+
+extern "C" int64_t pnerf_scan_workspace_bytes(int64_t n) { return scan_workspace_bytes(n + 1) + align_up((n + 1) * 4, 256); }
+
+extern "C" int pnerf_sample_compact(const uint8_t* sample_valid, int64_t n_slots, int* sample_ids, int* n_samples,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_slots < 0 || !sample_ids || !n_samples) return PNERF_ERR_ARG;
+    if (n_slots == 0) { PNERF_CUDA(cudaMemsetAsync(n_samples, 0, 4, st)); return PNERF_OK; }
+    if (!sample_valid || !workspace) return PNERF_ERR_ARG;
+    int64_t pos_bytes = align_up((n_slots + 1) * 4, 256);
+    if (workspace_bytes < pos_bytes + scan_workspace_bytes(n_slots)) return PNERF_ERR_WORKSPACE;
+    int* pos = (int*)workspace;
+    unsigned blocks = (unsigned)((n_slots + 255) / 256);
+    flags_to_i32_kernel<<<blocks, 256, 0, st>>>(sample_valid, n_slots, pos);
+    PNERF_LAUNCH_CHECK();
+    int rc = exclusive_scan_i32(pos, pos, n_slots, true, (char*)workspace + pos_bytes, workspace_bytes - pos_bytes, st);
+    if (rc) return rc;
+    scatter_ids_kernel<<<blocks, 256, 0, st>>>(sample_valid, pos, n_slots, sample_ids, n_samples);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_ray_compact(const uint8_t* sample_valid, int R, int SR, int8_t* ray_mask, int* ray_index,
+                                 int* n_rays, void* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (R < 0 || SR <= 0 || !n_rays) return PNERF_ERR_ARG;
+    if (R == 0) { PNERF_CUDA(cudaMemsetAsync(n_rays, 0, 4, st)); return PNERF_OK; }
+    if (!sample_valid || !ray_mask || !ray_index || !workspace) return PNERF_ERR_ARG;
+    int64_t pos_bytes = align_up(((int64_t)R + 1) * 4, 256);
+    if (workspace_bytes < pos_bytes + scan_workspace_bytes(R)) return PNERF_ERR_WORKSPACE;
+    int* pos = (int*)workspace;
+    ray_flags_kernel<<<(unsigned)(((int64_t)R * 32 + 255) / 256), 256, 0, st>>>(sample_valid, R, SR, ray_mask, pos);
+    PNERF_LAUNCH_CHECK();
+    int rc = exclusive_scan_i32(pos, pos, R, true, (char*)workspace + pos_bytes, workspace_bytes - pos_bytes, st);
+    if (rc) return rc;
+    scatter_rays_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(pos, ray_mask, R, ray_index, n_rays);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_gather_rays(const int* ray_index, int n_rays, int SR, int K, const int* sample_pidx,
+                                 const float* sample_loc, int* out_pidx, float* out_loc, void* stream) {
+    if (n_rays < 0) return PNERF_ERR_ARG;
+    if (n_rays == 0) return PNERF_OK;
+    int64_t total = (int64_t)n_rays * SR * (K + 3);
+    gather_rays_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ray_index, n_rays, SR, K, sample_pidx,
+                                                                                         sample_loc, out_pidx, out_loc);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_version(void) { return 100; }
+extern "C" const char* pnerf_last_cuda_error(void) { return g_last_error; }
+extern "C" int pnerf_device_check(void) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) return PNERF_ERR_CUDA;
+    return p.major == 10 ? PNERF_OK : PNERF_ERR_ARCH;
+}

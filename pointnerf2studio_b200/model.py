@@ -1,0 +1,403 @@
+"""Host-side mirror of the reference's plugin classes for the hot path.
+
+Same names, argument meaning and outputs as
+  pointnerf/nerfstudio/studio_model.py  (PointNerfConfig SM:61-118, PointNerf SM:122-504)
+  pointnerf/nerfstudio/studio_utils.py  (NeuralPoints SU:71-209, PointNeRFEncoding SU:47-68)
+but `get_outputs` runs on libpnerf_b200.so: grid built once per cloud version, sample selection +
+neighbour query + field networks + compositing as CUDA kernels, no per-call host syncs on the
+bf16 path.  Nerfstudio is not required: `PointNerf` is a plain nn.Module that accepts any object with
+`origins (R,3)`, `directions (R,3)`, `nears/fars (R,1)`, `metadata["camrotc2w"]`; the registration
+shim for `ns-train pointnerf-original` lives in nerfstudio_plugin.py.
+"""
+from __future__ import annotations
+
+import dataclasses
+import glob
+import os
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import Parameter
+
+from . import native
+
+
+@dataclass
+class RayBundle:
+    """Minimal stand-in for nerfstudio.cameras.rays.RayBundle (the fields SU:148-155 reads)."""
+    origins: torch.Tensor
+    directions: torch.Tensor
+    nears: torch.Tensor
+    fars: torch.Tensor
+    metadata: Dict[str, torch.Tensor]
+
+    def __len__(self):
+        return self.origins.shape[0]
+
+
+@dataclass
+class PointNerfConfig:
+    """Every field of the reference's PointNerfConfig (SM:61-118), same names and defaults."""
+    _target: Any = dataclasses.field(default_factory=lambda: PointNerf)
+    path_point_cloud: Optional[Path] = None
+    eval_num_rays_per_chunk: int = 4096
+    feat_grad: bool = True
+    conf_grad: bool = True
+    dir_grad: bool = True
+    color_grad: bool = True
+    num_pos_freqs: Optional[int] = 10
+    num_viewdir_freqs: Optional[int] = 4
+    num_feat_freqs: Optional[int] = 3
+    num_dist_freqs: Optional[int] = 5
+    agg_dist_pers: Optional[int] = 20
+    point_features_dim: Optional[int] = 32
+    point_color_mode: Optional[bool] = True
+    point_dir_mode: Optional[bool] = True
+    num_samples: int = 80
+    use_biased_sampler: bool = False
+    field_dim: int = 64
+    num_mlp_base_layers: Optional[int] = 2
+    num_mlp_head_layers: Optional[int] = 2
+    num_color_layers: Optional[int] = 3
+    num_alpha_layers: Optional[int] = 1
+    hidden_size: int = 256
+    hidden_size_color: int = 128
+    apply_pnt_mask: bool = True
+    act_super: bool = False
+    axis_weight: List[float] = dataclasses.field(default_factory=lambda: [1., 1., 1.])
+    kernel_size: List[int] = dataclasses.field(default_factory=lambda: [3, 3, 3])
+    vscale: List[float] = dataclasses.field(default_factory=lambda: [2, 2, 2])
+    vsize: List[float] = dataclasses.field(default_factory=lambda: [0.004, 0.004, 0.004])
+    query_size: List[float] = dataclasses.field(default_factory=lambda: [3, 3, 3])
+    ranges: List[float] = dataclasses.field(default_factory=lambda: [-1.200, -1.200, -1.200, 1.200, 1.200, 1.200])
+    z_depth_dim: int = 400
+    SR: int = 80
+    K: int = 8
+    max_o: int = 1000000
+    P: int = 12
+    NN: int = 2
+    gpu_maxthr: int = 1024
+    zero_epsilon: float = 1e-3
+    zero_one_loss_weights: float = 0.0001
+    loss_coefficients: Dict[str, float] = dataclasses.field(default_factory=dict)
+    # ---- additions of this implementation (not in the reference)
+    precision: str = "bf16"        # "fp32": SIMT exact-parity kernels; "bf16": tcgen05 tensor-core kernels
+    flow: str = "plugin"           # "plugin" (SM math) or "original" (PointAggregator/ray_march math)
+    jitter: float = 0.3            # SU:166 hard-codes 0.3 in train and eval
+
+    def __post_init__(self):
+        if self.path_point_cloud is not None and not Path(self.path_point_cloud).exists():
+            raise RuntimeError(f"PointCloud path {self.path_point_cloud} does not exist")
+        unsupported = (self.num_viewdir_freqs != 4 or self.num_feat_freqs != 3 or self.num_dist_freqs != 5
+                       or self.agg_dist_pers != 20 or self.point_features_dim != 32 or self.hidden_size != 256
+                       or self.hidden_size_color != 128 or self.num_mlp_base_layers != 2 or self.num_mlp_head_layers != 2
+                       or self.num_color_layers != 3 or not self.point_color_mode or not self.point_dir_mode
+                       or not self.apply_pnt_mask or list(self.axis_weight) != [1., 1., 1.])
+        if unsupported:
+            raise NotImplementedError("the CUDA kernels are specialised to the reference's shipped network shape "
+                                      "(SM:72-97 defaults); other shapes are out of scope (SURVEY.md section 8)")
+
+    def setup(self, **kwargs):
+        return self._target(self, **kwargs)
+
+
+def get_latest_epoch(resume_dir):
+    """SM:55-59."""
+    os.makedirs(resume_dir, exist_ok=True)
+    str_epoch = [f.split("_")[0] for f in os.listdir(resume_dir) if f.endswith("_states.pth")]
+    int_epoch = [int(i) for i in str_epoch]
+    return None if len(int_epoch) == 0 else str_epoch[int_epoch.index(max(int_epoch))]
+
+
+class PointNeRFEncoding(nn.Module):
+    """SU:47-68 (== positional_encoding NW:176-191); kept for API parity, the kernels encode in registers."""
+
+    def __init__(self, in_dim: int, num_frequencies: int, ori: bool = False):
+        super().__init__()
+        self.in_dim, self.num_frequencies, self.ori = in_dim, num_frequencies, ori
+
+    def forward(self, in_tensor, covs=None):
+        freq = (2 ** torch.arange(self.num_frequencies).float()).to(in_tensor.device)
+        pts = (in_tensor[..., None] * freq).reshape(in_tensor.shape[:-1] + (self.num_frequencies * in_tensor.shape[-1],))
+        if self.ori:
+            return torch.cat([in_tensor, torch.sin(pts), torch.cos(pts)], dim=-1)
+        return torch.stack([torch.sin(pts), torch.cos(pts)], dim=-1).reshape(pts.shape[:-1] + (pts.shape[-1] * 2,))
+
+
+class MLP(nn.Module):
+    """Parameter container with nerfstudio's MLP naming (`layers.{i}.weight/bias`)."""
+
+    def __init__(self, in_dim, num_layers, layer_width):
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, layer_width
+        self.layers = nn.ModuleList([nn.Linear(in_dim if i == 0 else layer_width, layer_width) for i in range(num_layers)])
+
+    def get_out_dim(self):
+        return self.out_dim
+
+
+class FieldHead(nn.Module):
+    """Parameter container with nerfstudio's FieldHead naming (`net.weight/bias`)."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.net = nn.Linear(in_dim, out_dim)
+
+
+class NeuralPoints(nn.Module):
+    """SU:71-209: owns the neural-point parameters and runs the querier.
+
+    Parameter names and shapes follow the reference (`points_embeding` keeps its spelling):
+    points_xyz (N,3) no grad, points_embeding (1,N,32), points_conf (1,N,1), points_dir (1,N,3),
+    points_color (1,N,3), points_Rw2c (3,3) no grad.
+    """
+
+    def __init__(self, state_dict, device, config: PointNerfConfig):
+        super().__init__()
+        self.config = config
+        self.device = torch.device(device)
+        self.points_xyz = Parameter(state_dict["neural_points.xyz"].to(self.device).float().contiguous(), requires_grad=False)
+        self.points_embeding = Parameter(state_dict["neural_points.points_embeding"].to(self.device).float().contiguous(),
+                                         requires_grad=config.feat_grad)
+        self.points_conf = Parameter(state_dict["neural_points.points_conf"].to(self.device).float().contiguous(),
+                                     requires_grad=config.conf_grad)
+        self.points_dir = Parameter(state_dict["neural_points.points_dir"].to(self.device).float().contiguous(),
+                                    requires_grad=config.dir_grad)
+        self.points_color = Parameter(state_dict["neural_points.points_color"].to(self.device).float().contiguous(),
+                                      requires_grad=config.color_grad)
+        self.points_Rw2c = Parameter(state_dict["neural_points.Rw2c"].to(self.device).float().contiguous(), requires_grad=False)
+        if self.points_Rw2c.dim() != 2:
+            raise NotImplementedError("per-point Rw2c (SU:207 second branch) is not produced by any shipped script")
+        self.kernel_size = np.asarray(config.kernel_size, dtype=np.int32)
+        self.query_size = np.asarray(config.query_size, dtype=np.int32)
+        self.radius_limit_np = np.asarray(4 * max(config.vsize[0], config.vsize[1])).astype(np.float32)   # SU:110
+        self.vscale_np = np.array(config.vscale, dtype=np.int32)
+        self.scaled_vsize_np = (config.vsize * self.vscale_np).astype(np.float32)                          # SU:112
+        self._grid = None
+        self._grid_key = None
+
+    # ---- grid cache: rebuilt only when the cloud changes (the reference rebuilds on every call, CU:314-365)
+    def grid(self) -> native.VoxelGrid:
+        key = (self.points_xyz.data_ptr(), self.points_xyz._version, tuple(self.points_xyz.shape))
+        if self._grid is None or self._grid_key != key:
+            frame = native.get_hyperparameters(self.points_xyz.detach(), self.config.vsize, self.config.vscale,
+                                               self.config.kernel_size, self.config.ranges)
+            self._grid = native.VoxelGrid(self.points_xyz.detach(), frame, self.config.P, self.config.query_size)
+            self._grid_key = key
+        return self._grid
+
+    def get_hyperparameters(self, vsize_np, point_xyz_w_tensor, ranges=None):
+        """SU:115-127, same return triple."""
+        f = native.get_hyperparameters(point_xyz_w_tensor, vsize_np, self.config.vscale, self.config.kernel_size, ranges)
+        ranges_tensor = torch.as_tensor(np.concatenate([f.lo, f.hi]), device=point_xyz_w_tensor.device)
+        return ranges_tensor, vsize_np, f.dim
+
+    @staticmethod
+    def camera_of(ray_bundle):
+        """SU:148-155: one camera per call; rotation and origin come from ray 0."""
+        rot = ray_bundle.metadata["camrotc2w"]
+        rot = rot[0].view(3, 3) if rot.shape[0] != 3 else rot
+        return ray_bundle.origins[0].detach().float().cpu().numpy(), rot.detach().float().cpu().numpy()
+
+    def coarse_t(self, R, near, far, jitter, generator=None):
+        """t mid-points of near_far_linear_ray_generation (RM:312-329): (D,) when jitter == 0 else (R,D)."""
+        D = self.config.z_depth_dim
+        dev = self.device
+        tau = torch.linspace(0, 1, D + 1, device=dev).view(1, -1)
+        edge = near * (1 - tau) + far * tau
+        seg = edge[..., 1:] - edge[..., :-1]
+        if jitter:
+            seg = seg * (1 + jitter * (torch.rand((1, R, D), device=dev, generator=generator)[0] - 0.5))
+        else:
+            seg = seg * (1 + jitter * (torch.full((1, D), 0.5, device=dev) - 0.5))
+        end = torch.cumsum(seg, dim=1)
+        end = near + torch.cat([torch.zeros((end.shape[0], 1), device=dev), end], dim=1)
+        t_mid = (end[:, :-1] + end[:, 1:]) / 2
+        return t_mid[0].contiguous() if not jitter else t_mid.contiguous()
+
+    def query(self, ray_bundle, jitter=None, generator=None, want_stats=False, near=None, far=None):
+        """Rows G0/G2/Q on the cached grid.  Returns (QueryResult, origin, R_c2w)."""
+        cfg = self.config
+        origin, R_c2w = self.camera_of(ray_bundle)
+        dirs = ray_bundle.directions.to(self.device).float().contiguous()
+        R = dirs.shape[0]
+        if near is None:
+            near, far = float(ray_bundle.nears[0]), float(ray_bundle.fars[0])           # SU:154-155
+        jitter = cfg.jitter if jitter is None else jitter
+        t = self.coarse_t(R, near, far, jitter, generator)
+        q = native.sample_and_query(self.grid(), R, cfg.z_depth_dim, cfg.SR, cfg.K, int(self.kernel_size[0]),
+                                    float(self.radius_limit_np), origin=origin, dirs=dirs, t_vals=t, want_stats=want_stats)
+        return q, origin, R_c2w, dirs
+
+    def forward(self, ray_bundle):
+        """Reference-shaped return value (SU:209): the 13 gathered tensors.  Compatibility API only --
+        `PointNerf.get_outputs` never materialises these (the kernels gather in registers)."""
+        cfg = self.config
+        q, origin, R_c2w, dirs = self.query(ray_bundle)
+        pidx, loc_w, ray_mask, ray_index, _ = native.compact_rays(q)
+        pidx, loc_w, ray_mask = pidx[None], loc_w[None], ray_mask[None]
+        o = torch.as_tensor(origin, device=self.device)[None]
+        Rc = torch.as_tensor(R_c2w, device=self.device)[None]
+
+        def pers(p):
+            cam = torch.sum((p - o[:, None, :] if p.dim() == 3 else p - o[:, None, None, :])[..., :, None] * Rc[0], dim=-2)
+            return torch.stack([cam[..., 0] / cam[..., 2], cam[..., 1] / cam[..., 2], cam[..., 2]], dim=-1)
+
+        mask = pidx >= 0
+        B, R2, SR, K = pidx.shape
+        flat = pidx.clamp(min=0).view(-1).long()
+        cat = torch.cat([self.points_xyz[None], pers(self.points_xyz[None]), self.points_embeding], dim=-1)
+        emb = torch.index_select(cat, 1, flat).view(B, R2, SR, K, -1)
+        col = torch.index_select(self.points_color, 1, flat).view(B, R2, SR, K, 3)
+        dr = torch.index_select(self.points_dir, 1, flat).view(B, R2, SR, K, 3)
+        cf = torch.index_select(self.points_conf, 1, flat).view(B, R2, SR, K, 1)
+        ray_dirs = dirs[ray_index.long()][None, :, None, :].expand(-1, -1, SR, -1).contiguous()
+        return (col, self.points_Rw2c, dr, emb[..., 6:], emb[..., 3:6], emb[..., :3], cf, pers(loc_w), loc_w, mask, ray_dirs,
+                cfg.vsize, ray_mask)
+
+
+class ConfCoefficient:
+    """What `outputs["conf_coefficient"]` carries in training (SM:396-397).  The reference stores the
+    gathered (1,R'',SR,K) tensor; here it is a handle so the loss kernel can read the indices directly."""
+
+    def __init__(self, conf, pidx, ray_mask, n_rays):
+        self.conf, self.pidx, self.ray_mask, self.n_rays = conf, pidx, ray_mask, n_rays
+
+    def materialize(self):
+        keep = self.ray_mask.bool()
+        c = self.conf.reshape(-1)[self.pidx[keep].clamp(min=0).long()]
+        return (c - (c - c.clamp(1e-4, 1)).detach())[None]
+
+
+class PointNerf(nn.Module):
+    """SM:122-504.  `get_outputs(ray_bundle)` -> {"coarse_raycolor" (R,3), "ray_mask" (R,) int8,
+    ["conf_coefficient"]}; `get_param_groups()` -> {"fields", "neural_points"}; `get_loss_dict`."""
+
+    def __init__(self, config: PointNerfConfig, cameras=None, state_dict=None, device="cuda", **kwargs):
+        super().__init__()
+        self.config = config
+        self.cameras = cameras
+        self._device = torch.device(device)
+        self._init_pointnerf(state_dict)
+        self.populate_modules()
+        self.to(self._device)
+
+    @property
+    def device(self):
+        return self._device
+
+    def _init_pointnerf(self, state_dict=None):
+        """SM:147-166: latest `<iter>_net_ray_marching.pth` under path_point_cloud."""
+        if state_dict is None:
+            if self.config.path_point_cloud is None:
+                raise RuntimeError("The point_cloud_path must be specified.")
+            from .checkpoint import load_point_cloud_checkpoint
+            state_dict = load_point_cloud_checkpoint(self.config.path_point_cloud)
+        self._loaded_state = state_dict
+        self.neural_points = NeuralPoints(state_dict, self._device, self.config)
+        self._point_initialized = True
+
+    def populate_modules(self):
+        """SM:169-237 (networks only; metrics are image-quality evaluation, out of scope)."""
+        c = self.config
+        self.direction_encoding = PointNeRFEncoding(2, c.num_viewdir_freqs, ori=True)
+        self.feature_encoding = PointNeRFEncoding(2, c.num_feat_freqs, ori=False)
+        self.dists_encoding = PointNeRFEncoding(2, c.num_dist_freqs, ori=False)
+        dist_dim = (4 if c.agg_dist_pers == 30 else 6) if c.agg_dist_pers > 9 else 3
+        dist_xyz_dim = dist_dim if c.num_dist_freqs == 0 else 2 * abs(c.num_dist_freqs) * dist_dim
+        mlp_in = 2 * c.num_feat_freqs * c.point_features_dim + dist_xyz_dim + c.point_features_dim
+        self.mlp_base = MLP(mlp_in, c.num_mlp_base_layers, c.hidden_size)
+        self.mlp_head = MLP(self.mlp_base.get_out_dim() + 3 + 4, c.num_mlp_head_layers, c.hidden_size)
+        self.mlp_color = MLP(self.mlp_head.get_out_dim() + 2 * c.num_viewdir_freqs * 3, c.num_color_layers, c.hidden_size_color)
+        self.field_output_color = FieldHead(self.mlp_color.get_out_dim(), 3)
+        self.field_output_density = FieldHead(self.mlp_head.get_out_dim(), 1)
+        self._background_color = torch.ones(3)
+        from .checkpoint import AGGREGATOR_MAP
+        if any(k.startswith("aggregator.") for k in self._loaded_state):     # original-flow checkpoint: reuse its MLPs
+            own = dict(self.named_parameters())
+            with torch.no_grad():
+                for new, old in AGGREGATOR_MAP.items():
+                    for s in ("weight", "bias"):
+                        own[f"{new}.{s}"].copy_(self._loaded_state[f"aggregator.{old}.{s}"])
+
+    def mlp_param_list(self):
+        out = []
+        own = dict(self.named_parameters())
+        for name, _, _ in native.MLP_PARAM_NAMES:
+            out += [own[name + ".weight"], own[name + ".bias"]]
+        return out
+
+    def get_param_groups(self) -> Dict[str, List[Parameter]]:
+        """SM:401-413."""
+        named = list(self.named_parameters())
+        return {"neural_points": [p for n, p in named if n.startswith("neural_points.points")],
+                "fields": [p for n, p in named if not n.startswith("neural_points.points")]}
+
+    def forward(self, ray_bundle):
+        return self.get_outputs(ray_bundle)
+
+    def get_outputs(self, ray_bundle, generator=None):
+        """SM:263-399."""
+        c = self.config
+        npnts = self.neural_points
+        q, origin, R_c2w, dirs = npnts.query(ray_bundle, generator=generator)
+        mode = native.make_mode(c.flow, training=self.training, bg=self._background_color.tolist(), vsize_z=c.vsize[2])
+        cfg = {"mode": mode, "camera": native.make_camera(origin, R_c2w)}
+        args = (cfg, q, dirs, npnts.points_xyz, npnts.points_Rw2c, npnts.points_embeding.view(-1, c.point_features_dim),
+                npnts.points_color.view(-1, 3), npnts.points_dir.view(-1, 3), npnts.points_conf.view(-1, 1))
+        if c.precision == "fp32":
+            rgb = native.render_f32(*args, self.mlp_param_list())
+        elif c.precision == "bf16":
+            from . import native_tc
+            rgb = native_tc.render_tc(*args, self.mlp_param_list())
+        else:
+            raise ValueError(c.precision)
+        lib = native._lib.load()
+        R, SR = q.sample_valid.shape
+        ray_mask = torch.empty((R,), dtype=torch.int8, device=self._device)
+        ray_index = torch.empty((max(R, 1),), dtype=torch.int32, device=self._device)
+        n_rays = torch.empty((1,), dtype=torch.int32, device=self._device)
+        ws_bytes = lib.pnerf_scan_workspace_bytes(R)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self._device)
+        native.check(lib.pnerf_ray_compact(native._ptr(q.sample_valid), R, SR, native._ptr(ray_mask), native._ptr(ray_index),
+                                           native._ptr(n_rays), native._ptr(ws), ws_bytes, native._stream()), "pnerf_ray_compact")
+        native.LAUNCHES["n"] += 3
+        out = {"coarse_raycolor": rgb, "ray_mask": ray_mask}
+        if self.training:
+            out["conf_coefficient"] = ConfCoefficient(npnts.points_conf, q.sample_pidx, ray_mask, n_rays)
+        self._last_query = q
+        return out
+
+    @torch.no_grad()
+    def get_outputs_for_camera_ray_bundle(self, ray_bundle, chunk=None):
+        """nerfstudio Model.get_outputs_for_camera_ray_bundle: slice into eval_num_rays_per_chunk rays (SC:25)."""
+        chunk = chunk or self.config.eval_num_rays_per_chunk
+        R = len(ray_bundle)
+        cols, masks = [], []
+        for i in range(0, R, chunk):
+            rb = RayBundle(ray_bundle.origins[i:i + chunk], ray_bundle.directions[i:i + chunk], ray_bundle.nears[i:i + chunk],
+                           ray_bundle.fars[i:i + chunk], ray_bundle.metadata)
+            o = self.get_outputs(rb)
+            cols.append(o["coarse_raycolor"])
+            masks.append(o["ray_mask"])
+        return {"coarse_raycolor": torch.cat(cols), "ray_mask": torch.cat(masks)}
+
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
+        """SM:415-431: MSE over the masked rays + 1e-6 and, in training, the zero-one confidence term."""
+        pred = outputs["coarse_raycolor"]
+        image = batch["image"].to(pred.device)
+        m = (outputs["ray_mask"] > 0).to(pred.dtype)[:, None]
+        mse = (((pred - image) ** 2) * m).sum() / (3.0 * m.sum())        # == MSELoss over masked_select rows
+        loss_dict = {"ray_masked_coarse_raycolor_loss": mse + 1e-6}
+        if self.training and "conf_coefficient" in outputs:
+            h = outputs["conf_coefficient"]
+            loss_dict["conf_coefficient_loss"] = native.conf_loss(h.conf.view(-1, 1), h.pidx, h.ray_mask, h.n_rays,
+                                                                  self.config.zero_epsilon, self.config.zero_one_loss_weights)
+        for k, v in self.config.loss_coefficients.items():                  # misc.scale_dict (SM:430)
+            if k in loss_dict:
+                loss_dict[k] = loss_dict[k] * v
+        return loss_dict

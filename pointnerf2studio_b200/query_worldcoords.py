@@ -1,0 +1,48 @@
+"""Drop-in for the reference's pybind module `query_worldcoords_cuda`
+(models/neural_points/cuda/query_worldcoords.cpp:33-50,76-78; call sites studio_utils.py:172-188 and
+point_query.py:86-93): the same 17-argument function, the same three return tensors.
+
+The reference rebuilds every table on every call and blocks the host five times; this shim caches the
+voxel grid per (cloud storage, version, frame) and needs one sync for the data-dependent R''.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import native
+
+_CACHE = {}
+
+
+def _as_np(x, dtype):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy().astype(dtype)
+    return np.asarray(x, dtype=dtype)
+
+
+def woord_query_grid_point_index(raypos_tensor, point_xyz_w_tensor, actual_numpoints_tensor, kernel_size, query_size,
+                                 SR, K, R, D, scaled_vdim, max_o, P, radius_limit, ranges, scaled_vsize,
+                                 kMaxThreadsPerBlock, NN):
+    """-> [sample_pidx i32 (B,R'',SR,K), sample_loc f32 (B,R'',SR,3), ray_mask i8 (B,R)], B = 1.
+
+    `actual_numpoints_tensor`, `max_o`, `kMaxThreadsPerBlock` and `NN` carry no semantics here: all N points
+    are used (the plugin always passes N, SU:160), no voxel is evicted, launch shapes are chosen per kernel and
+    NN is unused by the reference kernel too (CU:237)."""
+    assert point_xyz_w_tensor.shape[0] == 1, "the reference always runs with B = 1"
+    xyz = point_xyz_w_tensor[0]
+    ks, qs = _as_np(kernel_size, np.int32), _as_np(query_size, np.int32)
+    rng = _as_np(ranges, np.float32)
+    frame = native.GridFrame(lo=rng[:3].copy(), hi=rng[3:].copy(), sv=_as_np(scaled_vsize, np.float32),
+                             dim=_as_np(scaled_vdim, np.int32))
+    key = (xyz.data_ptr(), xyz._version, tuple(xyz.shape), frame.lo.tobytes(), frame.sv.tobytes(), frame.dim.tobytes(),
+           int(P), qs.tobytes())
+    grid = _CACHE.get(key)
+    if grid is None:
+        _CACHE.clear()
+        grid = _CACHE[key] = native.VoxelGrid(xyz, frame, int(P), qs)
+    radius = float(radius_limit.item()) if isinstance(radius_limit, torch.Tensor) else float(radius_limit)
+    raypos = raypos_tensor[0].contiguous().float()
+    q = native.sample_and_query(grid, int(R), int(D), int(SR), int(K), int(ks[0]), radius, raypos=raypos)
+    pidx, loc, ray_mask, _, _ = native.compact_rays(q)
+    return [pidx[None], loc[None], ray_mask[None]]

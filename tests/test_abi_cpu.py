@@ -1,0 +1,108 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol include/pnerf_b200.h
+declares (no compute calls), the host-side mirror keeps the reference's config surface, and the oracle is not
+reachable from the product package."""
+import ast
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    h = open(os.path.join(ROOT, "include", "pnerf_b200.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(pnerf_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pointnerf2studio_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
+    assert lib.pnerf_version() >= 100
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for s in syms:
+        assert re.search(rf"\bT {s}\b", nm), f"{s} is not an exported C symbol"
+
+
+def test_library_is_sm100a_only_and_torch_free():
+    from pointnerf2studio_b200 import _lib, build
+    build.build()
+    ldd = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in ldd and "c10" not in ldd
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_config_surface_matches_reference():
+    from pointnerf2studio_b200 import PointNerfConfig
+    c = PointNerfConfig()
+    ref_defaults = dict(eval_num_rays_per_chunk=4096, feat_grad=True, conf_grad=True, dir_grad=True, color_grad=True,
+                        num_pos_freqs=10, num_viewdir_freqs=4, num_feat_freqs=3, num_dist_freqs=5, agg_dist_pers=20,
+                        point_features_dim=32, point_color_mode=True, point_dir_mode=True, num_samples=80,
+                        use_biased_sampler=False, field_dim=64, num_mlp_base_layers=2, num_mlp_head_layers=2,
+                        num_color_layers=3, num_alpha_layers=1, hidden_size=256, hidden_size_color=128, apply_pnt_mask=True,
+                        act_super=False, axis_weight=[1., 1., 1.], kernel_size=[3, 3, 3], vscale=[2, 2, 2],
+                        vsize=[0.004] * 3, query_size=[3, 3, 3], ranges=[-1.2] * 3 + [1.2] * 3, z_depth_dim=400, SR=80, K=8,
+                        max_o=1000000, P=12, NN=2, gpu_maxthr=1024, zero_epsilon=1e-3, zero_one_loss_weights=0.0001)
+    for k, v in ref_defaults.items():
+        assert getattr(c, k) == v, k
+    with pytest.raises(NotImplementedError):
+        PointNerfConfig(hidden_size=128)
+
+
+def test_plugin_constants():
+    from pointnerf2studio_b200 import nerfstudio_plugin as p
+    assert p.METHOD_NAME == "pointnerf-original"
+    assert p.TRAINER_VALUES["eval_num_rays_per_chunk"] == 2304 and p.TRAINER_VALUES["train_num_rays_per_batch"] == 4096
+    assert abs(p.lr_lambda(1000000) - 0.1) < 1e-12 and p.lr_lambda(0) == 1.0
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pointnerf2studio_b200")
+    for fn in os.listdir(pkg):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), fn
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from pointnerf2studio_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.PnerfError):
+        _lib.load()
+
+
+def test_checkpoint_layout_roundtrip(tmp_path):
+    import torch
+    from pointnerf2studio_b200 import checkpoint
+    from pointnerf2studio_b200.synth import make_cloud
+    cloud = make_cloud(200, seed=3, radii=(0.03,))
+    sd = cloud.state_dict()
+    torch.save(sd, tmp_path / "0_net_ray_marching.pth")
+    torch.save({"total_steps": 0}, tmp_path / "0_states.pth")
+    torch.save(sd, tmp_path / "120_net_ray_marching.pth")
+    torch.save({"total_steps": 120}, tmp_path / "120_states.pth")
+    assert checkpoint.latest_epoch(str(tmp_path)) == "120"
+    back = checkpoint.load_point_cloud_checkpoint(tmp_path)
+    assert back["neural_points.points_embeding"].shape == (1, len(cloud.xyz), 32)
+    assert back["neural_points.xyz"].shape == (len(cloud.xyz), 3)
+    with pytest.raises(RuntimeError):
+        checkpoint.load_point_cloud_checkpoint(tmp_path / "missing")
