@@ -184,6 +184,11 @@ int pnerf_conf_loss(const float* conf, const int* sample_pidx, const int8_t* ray
                     float eps, float weight, const int* n_rays /* device R'' */, float* loss_out,
                     float* g_conf, float grad_scale, void* stream);
 
+/* ---------------------------------------------------------------- tensor-core plumbing self-test
+ * D[128xN] = A[128xK] * W[NxK]^T (bf16 in, fp32 out) through tcgen05.mma / TMEM / bulk async copy.
+ * A: bf16 row major; Wp: bf16 in the K-slab layout [K/8][N][8] (see csrc/umma.cuh). */
+int pnerf_umma_selftest(const void* A, const void* Wp, float* D, int N, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
