@@ -60,7 +60,7 @@ using namespace pnerf;
 extern "C" int pnerf_umma_selftest(const void* A, const void* Wp, float* D, int N, int K, void* stream) {
     if (!A || !Wp || !D || N < 16 || N > 256 || (N % 16) || K < 16 || (K % 16)) return PNERF_ERR_ARG;
     const size_t smem = (size_t)(128 + N) * K * 2;
-    if (smem > 200 * 1024) return PNERF_ERR_ARG;
+    if (smem > 226 * 1024) return PNERF_ERR_ARG;
     uint32_t cols = 32;
     while ((int)cols < N) cols <<= 1;
     PNERF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -26,6 +26,9 @@ from torch.nn import Parameter
 from . import native
 
 
+RENDER_RAYS_PER_LAUNCH = 1 << 21   # rays per query launch in full-image rendering (memory knob only)
+
+
 @dataclass
 class RayBundle:
     """Minimal stand-in for nerfstudio.cameras.rays.RayBundle (the fields SU:148-155 reads)."""
@@ -374,8 +377,11 @@ class PointNerf(nn.Module):
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, ray_bundle, chunk=None):
-        """nerfstudio Model.get_outputs_for_camera_ray_bundle: slice into eval_num_rays_per_chunk rays (SC:25)."""
-        chunk = chunk or self.config.eval_num_rays_per_chunk
+        """nerfstudio Model.get_outputs_for_camera_ray_bundle.  The reference slices the image into
+        eval_num_rays_per_chunk = 2304 rays (SC:25) and rebuilds its grid for each slice; chunking does not change
+        any pixel (rays are independent), so here `chunk` only bounds the rays per query launch (default: the whole
+        image) and the field kernels walk the compact list of valid samples in fixed-size pieces."""
+        chunk = chunk or RENDER_RAYS_PER_LAUNCH
         R = len(ray_bundle)
         cols, masks = [], []
         for i in range(0, R, chunk):
@@ -384,6 +390,8 @@ class PointNerf(nn.Module):
             o = self.get_outputs(rb)
             cols.append(o["coarse_raycolor"])
             masks.append(o["ray_mask"])
+        if len(cols) == 1:
+            return {"coarse_raycolor": cols[0], "ray_mask": masks[0]}
         return {"coarse_raycolor": torch.cat(cols), "ray_mask": torch.cat(masks)}
 
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:

@@ -130,11 +130,13 @@ def sample_and_query(grid: VoxelGrid, R: int, D: int, SR: int, K: int, kernel_si
     if raypos is None:
         assert dirs is not None and t_vals is not None and origin is not None
         t_stride = 0 if t_vals.dim() == 1 else D
-    check(lib.pnerf_sample_select(C.byref(grid.view), _ptr(raypos, torch.float32), _f3(origin) if origin is not None else None,
-                                  _ptr(dirs, torch.float32), _ptr(t_vals, torch.float32), t_stride, R, D, SR, _ptr(loc),
-                                  _ptr(cnt), _stream()), "pnerf_sample_select")
-    check(lib.pnerf_query(C.byref(grid.view), _ptr(loc), _ptr(cnt), R, SR, K, int(kernel_size0), C.c_float(float(radius)),
-                          _ptr(pidx), _ptr(valid), _ptr(stats), _stream()), "pnerf_query")
+    with Timers.span("select"):
+        check(lib.pnerf_sample_select(C.byref(grid.view), _ptr(raypos, torch.float32), _f3(origin) if origin is not None else None,
+                                      _ptr(dirs, torch.float32), _ptr(t_vals, torch.float32), t_stride, R, D, SR, _ptr(loc),
+                                      _ptr(cnt), _stream()), "pnerf_sample_select")
+    with Timers.span("query"):
+        check(lib.pnerf_query(C.byref(grid.view), _ptr(loc), _ptr(cnt), R, SR, K, int(kernel_size0), C.c_float(float(radius)),
+                              _ptr(pidx), _ptr(valid), _ptr(stats), _stream()), "pnerf_query")
     LAUNCHES["n"] += 2
     return QueryResult(loc, cnt, pidx, valid, stats)
 
@@ -229,33 +231,106 @@ def make_mlp(params: dict, cls=Mlp):
 
 
 # ---------------------------------------------------------------------------------------------- field + composite
+F32_EVAL_CHUNK = 131072   # samples per field launch when no activations are kept (workspace = 61 KB per sample at K=8)
+
+
+class Timers:
+    """Optional CUDA-event timers around named stages (bench.py turns them on; off = zero cost)."""
+    enabled = False
+    spans = []   # (name, start_event, end_event)
+
+    @classmethod
+    def span(cls, name):
+        return _Span(name) if cls.enabled else _NULL_SPAN
+
+    @classmethod
+    def collect(cls):
+        """-> {name: [ms, ...]} (call after torch.cuda.synchronize())."""
+        out = {}
+        for name, a, b in cls.spans:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        cls.spans = []
+        return out
+
+
+class _Span:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        self.b.record()
+        Timers.spans.append((self.name, self.a, self.b))
+        return False
+
+
+class _NullSpan:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_SPAN = _NullSpan()
+
+
+def _names():
+    return [n for _, w, b in MLP_PARAM_NAMES for n in (w, b)]
+
+
+def field_forward_f32(cfg, q: QueryResult, dirs, pts: Points, mlp: Mlp, ids, S: int, keep_workspace: bool):
+    """Launch the fp32 field networks over the compact sample list `ids[:S]`.  With keep_workspace the whole
+    list goes in one launch and the activation workspace is returned for the backward pass; otherwise the
+    list is processed in fixed-size chunks that reuse one workspace (full-image rendering)."""
+    lib = _lib.load()
+    R, SR, K = q.sample_pidx.shape
+    dev = dirs.device
+    mode, cam = cfg["mode"], cfg["camera"]
+    sigma = torch.zeros((R, SR), dtype=torch.float32, device=dev)
+    rgb = torch.zeros((R, SR, 3), dtype=torch.float32, device=dev)
+    step = S if keep_workspace else min(S, F32_EVAL_CHUNK)
+    ws_bytes = lib.pnerf_field_f32_workspace_bytes(step, K)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    with Timers.span("field"):
+        for s0 in range(0, S, max(step, 1)):
+            n = min(step, S - s0)
+            check(lib.pnerf_field_forward_f32(C.byref(pts), C.byref(cam), C.byref(mlp), C.byref(mode), _ptr(dirs),
+                                              _ptr(q.sample_loc), _ptr(q.sample_pidx), C.c_void_p(ids.data_ptr() + 4 * s0), n, SR,
+                                              K, _ptr(sigma), _ptr(rgb), _ptr(ws), ws_bytes, _stream()), "pnerf_field_forward_f32")
+            LAUNCHES["n"] += 11
+    return sigma, rgb, (ws if keep_workspace else None)
+
+
+def composite_forward(cfg, q: QueryResult, sigma, rgb):
+    lib = _lib.load()
+    R, SR, K = q.sample_pidx.shape
+    out = torch.empty((R, 3), dtype=torch.float32, device=sigma.device)
+    with Timers.span("composite"):
+        check(lib.pnerf_composite_forward(C.byref(cfg["camera"]), C.byref(cfg["mode"]), _ptr(q.sample_loc), _ptr(q.sample_valid),
+                                          _ptr(sigma), _ptr(rgb), R, SR, _ptr(out), None, None, _stream()), "pnerf_composite_forward")
+    LAUNCHES["n"] += 1
+    return out
+
+
 class _RenderF32(torch.autograd.Function):
     """fp32 path: field networks + step length + compositing as one autograd node."""
 
     @staticmethod
     def forward(ctx, cfg, q: QueryResult, dirs, xyz, Rw2c, embed, color, dirn, conf, *mlp_params):
-        lib = _lib.load()
-        R, SR, K = q.sample_pidx.shape
-        dev = dirs.device
-        mode: Mode = cfg["mode"]
-        cam: Camera = cfg["camera"]
-        names = [n for _, w, b in MLP_PARAM_NAMES for n in (w, b)]
-        params = dict(zip(names, [p.detach().contiguous() for p in mlp_params]))
+        params = dict(zip(_names(), [p.detach().contiguous() for p in mlp_params]))
         pts = make_points(xyz.detach(), embed.detach(), color.detach(), dirn.detach(), conf.detach(), Rw2c)
         mlp = make_mlp(params)
         ids, n_dev = compact_samples(q.sample_valid)
         S = int(n_dev.item())
-        sigma = torch.zeros((R, SR), dtype=torch.float32, device=dev)
-        rgb = torch.zeros((R, SR, 3), dtype=torch.float32, device=dev)
-        ws_bytes = lib.pnerf_field_f32_workspace_bytes(S, K)
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-        check(lib.pnerf_field_forward_f32(C.byref(pts), C.byref(cam), C.byref(mlp), C.byref(mode), _ptr(dirs), _ptr(q.sample_loc),
-                                          _ptr(q.sample_pidx), _ptr(ids), S, SR, K, _ptr(sigma), _ptr(rgb), _ptr(ws), ws_bytes,
-                                          _stream()), "pnerf_field_forward_f32")
-        out = torch.empty((R, 3), dtype=torch.float32, device=dev)
-        check(lib.pnerf_composite_forward(C.byref(cam), C.byref(mode), _ptr(q.sample_loc), _ptr(q.sample_valid), _ptr(sigma),
-                                          _ptr(rgb), R, SR, _ptr(out), None, None, _stream()), "pnerf_composite_forward")
-        LAUNCHES["n"] += 12
+        need_bwd = cfg.get("need_bwd", True) and any(ctx.needs_input_grad)
+        sigma, rgb, ws = field_forward_f32(cfg, q, dirs, pts, mlp, ids, S, keep_workspace=need_bwd)
+        out = composite_forward(cfg, q, sigma, rgb)
         ctx.cfg, ctx.q, ctx.S, ctx.ids, ctx.ws = cfg, q, S, ids, ws
         ctx.keep = (dirs, xyz, Rw2c, embed, color, dirn, conf, params, sigma, rgb)
         ctx.shapes = [p.shape for p in mlp_params]
@@ -291,12 +366,12 @@ class _RenderF32(torch.autograd.Function):
                                            _ptr(g_color), _ptr(g_dir), _ptr(g_conf), C.byref(gm), _ptr(ws), ws_bytes, _stream()),
               "pnerf_field_backward_f32")
         LAUNCHES["n"] += 30
-        names = [n for _, w, b in MLP_PARAM_NAMES for n in (w, b)]
-        mlp_grads = [grads[n].reshape(s) for n, s in zip(names, ctx.shapes)]
+        mlp_grads = [grads[n].reshape(s) for n, s in zip(_names(), ctx.shapes)]
         return (None, None, None, None, None, g_embed, g_color, g_dir, g_conf, *mlp_grads)
 
 
 def render_f32(cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, mlp_params):
+    cfg["need_bwd"] = torch.is_grad_enabled()
     return _RenderF32.apply(cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, *mlp_params)
 
 
