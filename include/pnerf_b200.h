@@ -166,6 +166,20 @@ int pnerf_field_backward_f32(const pnerf_points* pts_h, const pnerf_camera* cam_
                              float* g_dir, float* g_conf, const pnerf_mlp_grad* g_mlp_h, void* workspace,
                              int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------- field networks, tensor-core path (same rows)
+ * bf16 operands / fp32 accumulation on tcgen05 + TMEM: gather, encodings, mlp_base, mlp_head, density head and
+ * K-aggregation fused in one persistent kernel (no encoded input or activation ever reaches HBM), mlp_color +
+ * rgb head in a second one.  `wpack` is the bf16 K-slab copy of the seven weight matrices made by
+ * pnerf_tc_pack_weights (pnerf_tc_wpack_bytes() bytes; re-pack after every optimiser step).
+ * Inference-only (saves nothing); sigma / rgb as in pnerf_field_forward_f32. */
+int64_t pnerf_tc_wpack_bytes(void);
+int pnerf_tc_pack_weights(const pnerf_mlp* mlp_h, void* wpack, void* stream);
+int64_t pnerf_field_tc_workspace_bytes(int64_t n_samples);
+int pnerf_field_forward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const void* wpack,
+                           const pnerf_mode* mode_h, const float* dirs, const float* sample_loc, const int* sample_pidx,
+                           const int* sample_ids, int n_samples, int SR, int K, float* sigma, float* rgb, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------- step length + compositing (rows D, C, F)
  * Replaces SM:368-390 (+ nerfstudio RGBRenderer) and fill_invalid SM:491-504; original-flow twin
  * NPV:271-279 + ray_march RM:495-541.  One warp per ray, all R rays (missed rays -> bg).

@@ -81,6 +81,12 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(MlpGrad), C.c_void_p, C.c_int64, C.c_void_p]),
+    "pnerf_tc_wpack_bytes": (C.c_int64, []),
+    "pnerf_tc_pack_weights": (C.c_int, [C.POINTER(Mlp), C.c_void_p, C.c_void_p]),
+    "pnerf_field_tc_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "pnerf_field_forward_tc": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.c_void_p, C.POINTER(Mode),
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pnerf_composite_forward": (C.c_int, [C.POINTER(Camera), C.POINTER(Mode), C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pnerf_composite_backward": (C.c_int, [C.POINTER(Camera), C.POINTER(Mode), C.c_void_p, C.c_void_p, C.c_void_p,

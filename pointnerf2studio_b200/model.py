@@ -373,6 +373,7 @@ class PointNerf(nn.Module):
         if self.training:
             out["conf_coefficient"] = ConfCoefficient(npnts.points_conf, q.sample_pidx, ray_mask, n_rays)
         self._last_query = q
+        self._last_render = cfg.get("last")
         return out
 
     @torch.no_grad()
