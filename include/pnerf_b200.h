@@ -77,6 +77,16 @@ typedef struct {
 int pnerf_sample_select(const pnerf_grid_view* grid_h, const float* raypos, const float* origin_h,
                         const float* dirs, const float* t_vals, int t_stride, int R, int D, int SR,
                         float* sample_loc, int* sample_cnt, void* stream);
+/* Same, with the coarse t mid-points of near_far_linear_ray_generation (RM:312-329, called with jitter 0.3 at
+ * SU:166) generated in registers: segment j = (edge_{j+1} - edge_j) * (1 + jitter * (U - 0.5)), U = Philox4x32-10
+ * keyed by `seed` with counter (j/4, ray) -- the reference draws U with torch.rand, so jittered runs agree with it
+ * in distribution, not bit for bit; pnerf_coarse_t writes the very t (R,D) and U (R,D, optional) this kernel uses so
+ * that a checker can replay them through the t-table source above. */
+int pnerf_sample_select_jitter(const pnerf_grid_view* grid_h, const float* origin_h, const float* dirs, float near_t,
+                               float far_t, float jitter, uint64_t seed, int R, int D, int SR, float* sample_loc,
+                               int* sample_cnt, void* stream);
+int pnerf_coarse_t(float near_t, float far_t, float jitter, uint64_t seed, int R, int D, float* t_out, float* u_out,
+                   void* stream);
 
 /* ---------------------------------------------------------------- neighbour query (row Q)
  * Replaces query_neigh_along_ray_layered (CU:217-302): layer-truncated, bucket-capped,

@@ -1,15 +1,16 @@
-// Sample selection (rows G0/G2) and layered K-nearest query (row Q) -- replaces mask_raypos,
-// get_shadingloc, query_neigh_along_ray_layered and the torch glue between them
-// (query_worldcoords.cu:165-302, 368-422).
+// Sample selection (rows G0/G2) and layered K-nearest query (row Q) -- replaces near_far_linear_ray_generation,
+// mask_raypos, get_shadingloc, query_neigh_along_ray_layered and the torch glue between them
+// (diff_ray_marching.py:292-336, query_worldcoords.cu:165-302, 368-422).
 //
-// sample_select: one warp per ray walks the D coarse positions 32 at a time, probes the occupancy
-//   bitmask (L1/L2 resident), ballots the hits and compacts the first SR of them with popc prefixes.
-//   No (R,D) mask tensor, no cumsum, no masked_select, no host sync.
-// query: a group of Kp lanes (Kp = 8, 16 or 32 >= K) owns one sample, so a warp serves 32/Kp
-//   consecutive slots of one ray (neighbouring samples share cells -> L1 hits).  Candidates come as
-//   coalesced runs of 16-byte records (see grid.cu); the group keeps its K best sorted across lanes and
-//   inserts candidates with one ballot + one shuffle-up.  Shell by shell, stop when >= K in-radius
-//   candidates have been seen (CU:300).
+// sample_select: one warp per ray.  A lane owns 4 consecutive coarse positions of each 128-position chunk; the
+//   jittered t mid-points are generated in registers (Philox4x32-10 keyed by (seed, ray, j/4), warp scan of the
+//   segment lengths), the ray is clipped against the grid box first so only positions inside it are probed
+//   against the occupancy bitmask (L1/L2 resident), and the first SR hits are compacted with a warp prefix sum.
+//   No (R,D,3) position tensor, no (R,D) mask, no cumsum / masked_select, no host sync.
+// query: one THREAD per sample slot, a warp = 32 consecutive slots of one ray (neighbouring samples share
+//   cells -> L1 hits).  Candidates come as runs of 16-byte records sorted by (cell, index) (see grid.cu); the
+//   thread keeps its K best in registers as a sorted list with a branch-free unrolled insertion.  Shell by shell,
+//   stop when >= K in-radius candidates have been seen (CU:300).
 #include "pnerf_common.cuh"
 
 namespace pnerf {
@@ -22,38 +23,152 @@ __device__ __forceinline__ bool occ_probe(const Frame& f, const uint32_t* __rest
     return (__ldg(occ + (id >> 5)) >> (id & 31)) & 1u;
 }
 
+// ------------------------------------------------------------------------------------------------ coarse t
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }   // [0,1), 24 bits
+
+struct TGen { float near, far, jitter; uint32_t seed_lo, seed_hi; };
+
+// t edge j of RM:313-315: near * (1 - tau_j) + far * tau_j, tau = linspace(0, 1, D + 1) (torch: start + i*step for the
+// first half, end - (steps-1-i)*step for the second)
+__device__ __forceinline__ float t_edge(const TGen& g, int j, int D) {
+    const float step = 1.f / (float)D;
+    const float tau = (j < (D + 1) / 2) ? __fmul_rn(step, (float)j) : __fsub_rn(1.f, __fmul_rn(step, (float)(D - j)));
+    return __fadd_rn(__fmul_rn(g.near, __fsub_rn(1.f, tau)), __fmul_rn(g.far, tau));
+}
+
+// The four t mid-points [jb, jb+4) of ray r (jb = j0 + 4*lane) of RM:312-329 with jitter; `carry` = sum of the segment
+// lengths before j0 (warp-uniform), updated to include this chunk.  Positions with j >= D get t = +inf.
+__device__ __forceinline__ void chunk_t(const TGen& g, int r, int jb, int D, int lane, float& carry, float (&t)[4]) {
+    float seg[4];
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(jb >> 2), (uint32_t)r, 0u, 0u), make_uint2(g.seed_lo, g.seed_hi));
+    const uint32_t rv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+    float e0 = jb < D ? t_edge(g, jb, D) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int j = jb + i;
+        float s = 0.f;
+        if (j < D) {
+            const float e1 = t_edge(g, j + 1, D);
+            s = __fmul_rn(__fsub_rn(e1, e0), __fadd_rn(1.f, __fmul_rn(g.jitter, __fsub_rn(u01(rv[i]), 0.5f))));   // RM:318-322
+            e0 = e1;
+        }
+        seg[i] = s;
+    }
+    const float tot = (seg[0] + seg[1]) + (seg[2] + seg[3]);
+    float inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    float run = carry + (inc - tot);                 // cumsum before this lane's first segment
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float end0 = g.near + run;             // RM:324-326
+        run += seg[i];
+        const float end1 = g.near + run;
+        t[i] = (jb + i < D) ? 0.5f * (end0 + end1) : INFINITY;   // RM:327
+    }
+}
+
+// Ray / grid-box slab test with half a voxel of margin: positions with t outside [ta, tb] are outside the grid and can
+// never hit (CU:181-185), so they are not probed.
+__device__ __forceinline__ void clip_ray(const Frame& f, const float o[3], const float d[3], float& ta, float& tb) {
+    ta = -INFINITY; tb = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float lo = f.lo[a] - 0.5f * f.sv[a], hi = f.lo[a] + ((float)f.dim[a] + 0.5f) * f.sv[a];
+        if (fabsf(d[a]) > 1e-12f) {
+            const float t1 = (lo - o[a]) / d[a], t2 = (hi - o[a]) / d[a];
+            ta = fmaxf(ta, fminf(t1, t2));
+            tb = fminf(tb, fmaxf(t1, t2));
+        } else if (o[a] < lo || o[a] > hi) {
+            ta = INFINITY; tb = -INFINITY;
+        }
+    }
+    const float pad = 1e-4f * fmaxf(fabsf(ta), fabsf(tb));
+    if (ta <= tb) { ta -= pad; tb += pad; }
+}
+
+// MODE 0: explicit positions raypos (R,D,3); 1: t table (t_stride 0 or D); 2: jittered t generated in registers
+template <int MODE>
 __global__ void __launch_bounds__(256) sample_select_kernel(Frame f, const uint32_t* __restrict__ occ,
                                                              const float* __restrict__ raypos, float ox, float oy, float oz,
                                                              const float* __restrict__ dirs, const float* __restrict__ t_vals,
-                                                             int t_stride, int R, int D, int SR,
+                                                             int t_stride, TGen gen, int R, int D, int SR,
                                                              float* __restrict__ sample_loc, int* __restrict__ sample_cnt) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
-        float dx = 0.f, dy = 0.f, dz = 0.f;
-        if (!raypos) { dx = dirs[3 * (int64_t)r]; dy = dirs[3 * (int64_t)r + 1]; dz = dirs[3 * (int64_t)r + 2]; }
+        float d[3] = {0.f, 0.f, 0.f};
+        float ta = -INFINITY, tb = INFINITY;
+        if (MODE != 0) {
+            d[0] = __ldg(dirs + 3 * (int64_t)r); d[1] = __ldg(dirs + 3 * (int64_t)r + 1); d[2] = __ldg(dirs + 3 * (int64_t)r + 2);
+            const float o[3] = {ox, oy, oz};
+            clip_ray(f, o, d, ta, tb);
+        }
         float* loc = sample_loc + (int64_t)r * SR * 3;
         int n = 0;
-        for (int j0 = 0; j0 < D && n < SR; j0 += 32) {
-            const int j = j0 + lane;
-            float x = 0.f, y = 0.f, z = 0.f;
-            bool hit = false;
-            if (j < D) {
-                if (raypos) {
-                    const float* p = raypos + ((int64_t)r * D + j) * 3;
-                    x = p[0]; y = p[1]; z = p[2];
-                } else {
-                    const float t = t_vals[(int64_t)r * t_stride + j];
-                    x = __fadd_rn(ox, __fmul_rn(dx, t));   // campos + raydir * t, two roundings (RM:330)
-                    y = __fadd_rn(oy, __fmul_rn(dy, t));
-                    z = __fadd_rn(oz, __fmul_rn(dz, t));
+        float carry = 0.f;
+        if (ta <= tb) {
+            for (int j0 = 0; j0 < D && n < SR; j0 += 128) {
+                const int jb = j0 + 4 * lane;
+                float t[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+                if (MODE == 2) {
+                    if (gen.near + carry > tb) break;                     // every later position is behind the box (warp-uniform)
+                    chunk_t(gen, r, jb, D, lane, carry, t);
+                } else if (MODE == 1) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (jb + i < D) t[i] = __ldg(t_vals + (int64_t)r * t_stride + jb + i);
                 }
-                hit = occ_probe(f, occ, x, y, z);
+                float px[4], py[4], pz[4];
+                unsigned hits = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    bool probe = jb + i < D;
+                    if (MODE == 0) {
+                        if (probe) {
+                            const float* p = raypos + ((int64_t)r * D + jb + i) * 3;
+                            px[i] = __ldg(p); py[i] = __ldg(p + 1); pz[i] = __ldg(p + 2);
+                        }
+                    } else {
+                        probe = probe && t[i] >= ta && t[i] <= tb;
+                        px[i] = __fadd_rn(ox, __fmul_rn(d[0], t[i]));     // campos + raydir * t, two roundings (RM:330)
+                        py[i] = __fadd_rn(oy, __fmul_rn(d[1], t[i]));
+                        pz[i] = __fadd_rn(oz, __fmul_rn(d[2], t[i]));
+                    }
+                    if (probe && occ_probe(f, occ, px[i], py[i], pz[i])) hits |= 1u << i;
+                }
+                if (__ballot_sync(0xffffffffu, hits != 0) == 0) continue;
+                const int c = __popc(hits);
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                int slot = n + inc - c;
+                n += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if ((hits >> i) & 1u) {
+                        if (slot < SR) { loc[3 * slot] = px[i]; loc[3 * slot + 1] = py[i]; loc[3 * slot + 2] = pz[i]; }
+                        slot++;
+                    }
+                }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            const int slot = n + __popc(m & ((1u << lane) - 1u));
-            if (hit && slot < SR) { loc[3 * slot] = x; loc[3 * slot + 1] = y; loc[3 * slot + 2] = z; }
-            n += __popc(m);
         }
         n = min(n, SR);
         for (int e = 3 * n + lane; e < 3 * SR; e += 32) loc[e] = 0.f;   // unfilled slots stay (0,0,0) (CU:383)
@@ -61,94 +176,79 @@ __global__ void __launch_bounds__(256) sample_select_kernel(Frame f, const uint3
     }
 }
 
-// ------------------------------------------------------------------------------------------------ query
-struct Best {          // one entry of the group's sorted K-best list, distributed one per lane
-    uint32_t d2;       // float bits of d2 (>= 0, so unsigned order == float order); 0xffffffff = empty
-    uint32_t ord;      // visit order inside the sample: (shell << 24) | (run << 12) | position
-    int idx;
-};
-
-template <int KP>
-__device__ __forceinline__ void group_insert(Best& b, uint32_t cd2, uint32_t cord, int cidx, unsigned gmask, int glane,
-                                             int gshift) {
-    const bool before = (b.d2 < cd2) || (b.d2 == cd2 && b.ord < cord);   // my entry stays ahead of the candidate
-    const int pos = __popc((__ballot_sync(gmask, before) >> gshift) & (KP == 32 ? 0xffffffffu : ((1u << KP) - 1u)));
-    const uint32_t ud2 = __shfl_up_sync(gmask, b.d2, 1, KP);
-    const uint32_t uord = __shfl_up_sync(gmask, b.ord, 1, KP);
-    const int uidx = __shfl_up_sync(gmask, b.idx, 1, KP);
-    if (glane > pos) { b.d2 = ud2; b.ord = uord; b.idx = uidx; }
-    else if (glane == pos) { b.d2 = cd2; b.ord = cord; b.idx = cidx; }
-}
-
-// Scan one run of records [a, b) for the group's sample.
-template <int KP>
-__device__ __forceinline__ void scan_run(const float4* __restrict__ recs, int a, int b, float qx, float qy, float qz,
-                                         float r2, uint32_t ord_base, int K, Best& best, int& seen, unsigned gmask,
-                                         int glane, int gshift, unsigned long long& n_cand) {
-    for (int base = a; base < b; base += KP) {
-        const int i = base + glane;
-        uint32_t cd2 = 0xffffffffu;
-        int cidx = -1;
-        if (i < b) {
-            const float4 rec = __ldg(recs + i);
-            const float dx = __fsub_rn(rec.x, qx), dy = __fsub_rn(rec.y, qy), dz = __fsub_rn(rec.z, qz);
-            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));   // CU:271 as nvcc contracts it
-            if (r2 == 0.f || d2 <= r2) { cd2 = __float_as_uint(d2); cidx = __float_as_int(rec.w) & 0x0fffffff; }
-        }
-        unsigned m = (__ballot_sync(gmask, cidx >= 0) >> gshift) & (KP == 32 ? 0xffffffffu : ((1u << KP) - 1u));
-        seen += __popc(m);
-        n_cand += (glane == 0) ? (unsigned long long)(min(b, base + KP) - base) : 0ull;
-        while (m) {   // group-uniform loop: insert the in-radius candidates in visit order
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t sd2 = __shfl_sync(gmask, cd2, src, KP);
-            const int sidx = __shfl_sync(gmask, cidx, src, KP);
-            const uint32_t sord = ord_base + (uint32_t)(base - a + src);
-            // cheap reject: not better than the current K-th (lane K-1 holds it)
-            const uint32_t wd2 = __shfl_sync(gmask, best.d2, K - 1, KP);
-            const uint32_t word = __shfl_sync(gmask, best.ord, K - 1, KP);
-            if (sd2 < wd2 || (sd2 == wd2 && sord < word)) group_insert<KP>(best, sd2, sord, sidx, gmask, glane, gshift);
+// Test / oracle hook: the t table (R,D) and the uniforms (R,D) that MODE 2 uses, computed by the same device code.
+__global__ void __launch_bounds__(256) coarse_t_kernel(TGen gen, int R, int D, float* __restrict__ t_out, float* __restrict__ u_out) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
+        float carry = 0.f;
+        for (int j0 = 0; j0 < D; j0 += 128) {
+            const int jb = j0 + 4 * lane;
+            float t[4];
+            chunk_t(gen, r, jb, D, lane, carry, t);
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)(jb >> 2), (uint32_t)r, 0u, 0u), make_uint2(gen.seed_lo, gen.seed_hi));
+            const uint32_t rv[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (jb + i < D) {
+                    t_out[(int64_t)r * D + jb + i] = t[i];
+                    if (u_out) u_out[(int64_t)r * D + jb + i] = u01(rv[i]);
+                }
         }
     }
 }
 
-template <int KP>
-__global__ void __launch_bounds__(256) query_kernel(Frame f, const int* __restrict__ cell_start,
+// ------------------------------------------------------------------------------------------------ query
+// Sorted K-best list in registers; strict '<' keeps the earlier-visited candidate ahead on equal d2, so the list is
+// ordered by (d2, visit order) -- the tie-break rule of include/pnerf_b200.h.
+template <int KMAX>
+__device__ __forceinline__ void list_insert(float (&bd2)[KMAX], int (&bidx)[KMAX], float d2, int idx) {
+#pragma unroll
+    for (int i = KMAX - 1; i > 0; --i) {
+        const bool shift = d2 < bd2[i - 1];
+        const bool here = !shift && d2 < bd2[i];
+        bidx[i] = shift ? bidx[i - 1] : (here ? idx : bidx[i]);
+        bd2[i] = shift ? bd2[i - 1] : (here ? d2 : bd2[i]);
+    }
+    if (d2 < bd2[0]) { bd2[0] = d2; bidx[0] = idx; }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) query_kernel(Frame f, const int* __restrict__ cell_start,
                                                      const float4* __restrict__ recs, const float* __restrict__ sample_loc,
                                                      const int* __restrict__ sample_cnt, int R, int SR, int K, int layers,
                                                      float r2, int* __restrict__ sample_pidx, uint8_t* __restrict__ sample_valid,
                                                      unsigned long long* __restrict__ stats) {
-    constexpr int GPW = 32 / KP;                       // groups (samples) per warp
     const int lane = threadIdx.x & 31;
-    const int glane = lane % KP, gid = lane / KP, gshift = gid * KP;
-    const unsigned gmask = (KP == 32) ? 0xffffffffu : (((1u << KP) - 1u) << gshift);
-    const int groups_per_ray = (SR + GPW - 1) / GPW;   // warp w serves slots [w%gpr * GPW, +GPW) of ray w/gpr
-    const int64_t n_warps_work = (int64_t)R * groups_per_ray;
+    const int cpr = (SR + 31) >> 5;                    // 32-slot chunks per ray
+    const int64_t n_tasks = (int64_t)R * cpr;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_vis = 0, n_cand = 0;
-    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_warps_work; w += warps) {
-        const int r = (int)(w / groups_per_ray);
-        const int slot = (int)(w % groups_per_ray) * GPW + gid;
-        if (slot >= SR) continue;                      // group-uniform
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_tasks; w += warps) {
+        const int r = (int)(w / cpr);
+        const int slot = (int)(w % cpr) * 32 + lane;
+        if (slot >= SR) continue;
         const int64_t sid = (int64_t)r * SR + slot;
-        Best best = {0xffffffffu, 0xffffffffu, -1};
-        int seen = 0;
-        if (slot < sample_cnt[r]) {
-            const float qx = sample_loc[3 * sid], qy = sample_loc[3 * sid + 1], qz = sample_loc[3 * sid + 2];
+        float bd2[KMAX];
+        int bidx[KMAX];
+#pragma unroll
+        for (int i = 0; i < KMAX; i++) { bd2[i] = INFINITY; bidx[i] = -1; }
+        if (slot < __ldg(sample_cnt + r)) {
+            const float qx = __ldg(sample_loc + 3 * sid), qy = __ldg(sample_loc + 3 * sid + 1), qz = __ldg(sample_loc + 3 * sid + 2);
             int vx, vy, vz;
             if (voxel_of(f, qx, qy, qz, vx, vy, vz)) {
+                int seen = 0;
                 for (int shell = 0; shell < layers; shell++) {
-                    uint32_t run = 0;
                     for (int dx = -shell; dx <= shell; dx++) {
                         const int x = vx + dx;
+                        if (x < 0 || x >= f.dim[0]) continue;
                         for (int dy = -shell; dy <= shell; dy++) {
                             const int y = vy + dy;
-                            const bool in_xy = (x >= 0) && (x < f.dim[0]) && (y >= 0) && (y < f.dim[1]);
+                            if (y < 0 || y >= f.dim[1]) continue;
                             const bool rim = max(abs(dx), abs(dy)) == shell;   // whole z range belongs to this shell
                             // rim rows: one run z in [vz-shell, vz+shell]; inner rows: two single cells z = vz -+ shell
                             const int parts = rim ? 1 : 2;
-                            for (int part = 0; part < parts; part++, run++) {
-                                if (!in_xy) continue;
+                            for (int part = 0; part < parts; part++) {
                                 int z0, z1;
                                 if (rim) { z0 = vz - shell; z1 = vz + shell; }
                                 else { z0 = z1 = part == 0 ? vz - shell : vz + shell; }
@@ -156,9 +256,17 @@ __global__ void __launch_bounds__(256) query_kernel(Frame f, const int* __restri
                                 if (z0 > z1) continue;
                                 const int c0 = cell_lin(f, x, y, z0);
                                 const int a = __ldg(cell_start + c0), b = __ldg(cell_start + c0 + (z1 - z0) + 1);
-                                if (glane == 0) n_vis += (unsigned long long)(z1 - z0 + 1);
-                                scan_run<KP>(recs, a, b, qx, qy, qz, r2, ((uint32_t)shell << 24) | (run << 12), K, best, seen,
-                                             gmask, glane, gshift, n_cand);
+                                n_vis += (unsigned long long)(z1 - z0 + 1);
+                                n_cand += (unsigned long long)(b - a);
+                                for (int i = a; i < b; i++) {
+                                    const float4 rec = __ldg(recs + i);
+                                    const float ex = __fsub_rn(rec.x, qx), ey = __fsub_rn(rec.y, qy), ez = __fsub_rn(rec.z, qz);
+                                    const float d2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));   // CU:271 as nvcc contracts it
+                                    if (r2 == 0.f || d2 <= r2) {
+                                        seen++;
+                                        if (d2 < bd2[KMAX - 1]) list_insert<KMAX>(bd2, bidx, d2, __float_as_int(rec.w) & 0x0fffffff);
+                                    }
+                                }
                             }
                         }
                     }
@@ -166,8 +274,17 @@ __global__ void __launch_bounds__(256) query_kernel(Frame f, const int* __restri
                 }
             }
         }
-        if (glane < K) sample_pidx[sid * K + glane] = best.idx;
-        if (glane == 0) sample_valid[sid] = best.idx >= 0 ? 1 : 0;
+        int* out = sample_pidx + sid * K;
+        if (K == KMAX && (KMAX % 4) == 0) {
+#pragma unroll
+            for (int i = 0; i < KMAX; i += 4)
+                *reinterpret_cast<int4*>(out + i) = make_int4(bidx[i], bidx[i + 1], bidx[i + 2], bidx[i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < KMAX; i++)
+                if (i < K) out[i] = bidx[i];
+        }
+        sample_valid[sid] = bidx[0] >= 0 ? 1 : 0;
     }
     if (stats) {
 #pragma unroll
@@ -177,6 +294,12 @@ __global__ void __launch_bounds__(256) query_kernel(Frame f, const int* __restri
         }
         if (lane == 0 && (n_vis | n_cand)) { atomicAdd(stats, n_vis); atomicAdd(stats + 1, n_cand); }
     }
+}
+
+int ray_warps_grid(int R) {
+    const int64_t b = ((int64_t)R * 32 + 255) / 256;
+    const int64_t cap = (int64_t)kSMs * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
 }  // namespace
@@ -192,10 +315,40 @@ extern "C" int pnerf_sample_select(const pnerf_grid_view* g, const float* raypos
     if (!sample_loc || !sample_cnt || !g->occ_bits) return PNERF_ERR_ARG;
     if (!raypos && (!origin_h || !dirs || !t_vals || (t_stride != 0 && t_stride != D))) return PNERF_ERR_ARG;
     const Frame f = frame_of(g);
-    const int blocks = (int)min((int64_t)kSMs * 8, ((int64_t)R * 32 + 255) / 256);
-    sample_select_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(f, g->occ_bits, raypos, raypos ? 0.f : origin_h[0],
-                                                                  raypos ? 0.f : origin_h[1], raypos ? 0.f : origin_h[2], dirs,
-                                                                  t_vals, t_stride, R, D, SR, sample_loc, sample_cnt);
+    const TGen gen = {0.f, 0.f, 0.f, 0u, 0u};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (raypos)
+        sample_select_kernel<0><<<ray_warps_grid(R), 256, 0, st>>>(f, g->occ_bits, raypos, 0.f, 0.f, 0.f, nullptr, nullptr, 0, gen, R, D, SR,
+                                                                  sample_loc, sample_cnt);
+    else
+        sample_select_kernel<1><<<ray_warps_grid(R), 256, 0, st>>>(f, g->occ_bits, nullptr, origin_h[0], origin_h[1], origin_h[2], dirs,
+                                                                  t_vals, t_stride, gen, R, D, SR, sample_loc, sample_cnt);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_sample_select_jitter(const pnerf_grid_view* g, const float* origin_h, const float* dirs, float near, float far,
+                                          float jitter, uint64_t seed, int R, int D, int SR, float* sample_loc, int* sample_cnt,
+                                          void* stream) {
+    if (!g || R < 0 || D <= 0 || SR <= 0 || !(far > near)) return PNERF_ERR_ARG;
+    if (R == 0) return PNERF_OK;
+    if (!sample_loc || !sample_cnt || !g->occ_bits || !origin_h || !dirs) return PNERF_ERR_ARG;
+    const Frame f = frame_of(g);
+    const TGen gen = {near, far, jitter, (uint32_t)seed, (uint32_t)(seed >> 32)};
+    sample_select_kernel<2><<<ray_warps_grid(R), 256, 0, (cudaStream_t)stream>>>(f, g->occ_bits, nullptr, origin_h[0], origin_h[1],
+                                                                                origin_h[2], dirs, nullptr, 0, gen, R, D, SR,
+                                                                                sample_loc, sample_cnt);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_coarse_t(float near, float far, float jitter, uint64_t seed, int R, int D, float* t_out, float* u_out,
+                              void* stream) {
+    if (R < 0 || D <= 0 || !(far > near)) return PNERF_ERR_ARG;
+    if (R == 0) return PNERF_OK;
+    if (!t_out) return PNERF_ERR_ARG;
+    const TGen gen = {near, far, jitter, (uint32_t)seed, (uint32_t)(seed >> 32)};
+    coarse_t_kernel<<<ray_warps_grid(R), 256, 0, (cudaStream_t)stream>>>(gen, R, D, t_out, u_out);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }
@@ -210,17 +363,17 @@ extern "C" int pnerf_query(const pnerf_grid_view* g, const float* sample_loc, co
     if (!sample_loc || !sample_cnt || !sample_pidx || !sample_valid || !g->cell_start || !g->recs) return PNERF_ERR_ARG;
     const Frame f = frame_of(g);
     const float r2 = radius * radius;            // CU:410, fp32 on the host
-    const int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
-    const int64_t warps = (int64_t)R * ((SR + 32 / KP - 1) / (32 / KP));
-    const int blocks = (int)min((int64_t)kSMs * 16, (warps * 32 + 255) / 256);
+    const int64_t tasks = (int64_t)R * ((SR + 31) / 32);
+    const int blocks = (int)min((int64_t)kSMs * 16, (tasks * 32 + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* recs = (const float4*)g->recs;
-    if (KP == 8)
-        query_kernel<8><<<blocks, 256, 0, st>>>(f, g->cell_start, recs, sample_loc, sample_cnt, R, SR, K, layers, r2, sample_pidx, sample_valid, stats);
-    else if (KP == 16)
-        query_kernel<16><<<blocks, 256, 0, st>>>(f, g->cell_start, recs, sample_loc, sample_cnt, R, SR, K, layers, r2, sample_pidx, sample_valid, stats);
-    else
-        query_kernel<32><<<blocks, 256, 0, st>>>(f, g->cell_start, recs, sample_loc, sample_cnt, R, SR, K, layers, r2, sample_pidx, sample_valid, stats);
+#define PNERF_LAUNCH_Q(KM) \
+    query_kernel<KM><<<blocks, 128, 0, st>>>(f, g->cell_start, recs, sample_loc, sample_cnt, R, SR, K, layers, r2, sample_pidx, sample_valid, stats)
+    if (K <= 4) PNERF_LAUNCH_Q(4);
+    else if (K <= 8) PNERF_LAUNCH_Q(8);
+    else if (K <= 16) PNERF_LAUNCH_Q(16);
+    else PNERF_LAUNCH_Q(32);
+#undef PNERF_LAUNCH_Q
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }

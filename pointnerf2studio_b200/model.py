@@ -91,6 +91,7 @@ class PointNerfConfig:
     precision: str = "bf16"        # "fp32": SIMT exact-parity kernels; "bf16": tcgen05 tensor-core kernels
     flow: str = "plugin"           # "plugin" (SM math) or "original" (PointAggregator/ray_march math)
     jitter: float = 0.3            # SU:166 hard-codes 0.3 in train and eval
+    jitter_seed: int = 0           # Philox key (high word) of the in-kernel jitter; the low word counts calls
 
     def __post_init__(self):
         if self.path_point_cloud is not None and not Path(self.path_point_cloud).exists():
@@ -182,6 +183,8 @@ class NeuralPoints(nn.Module):
         self.scaled_vsize_np = (config.vsize * self.vscale_np).astype(np.float32)                          # SU:112
         self._grid = None
         self._grid_key = None
+        self._jitter_calls = 0
+        self._last_jitter = None
 
     # ---- grid cache: rebuilt only when the cloud changes (the reference rebuilds on every call, CU:314-365)
     def grid(self) -> native.VoxelGrid:
@@ -231,7 +234,16 @@ class NeuralPoints(nn.Module):
         if near is None:
             near, far = float(ray_bundle.nears[0]), float(ray_bundle.fars[0])           # SU:154-155
         jitter = cfg.jitter if jitter is None else jitter
-        t = self.coarse_t(R, near, far, jitter, generator)
+        if jitter and generator is None:
+            # jittered t generated inside the selection kernel (Philox keyed by a per-call seed): no (R,D) tensor at all
+            self._jitter_calls += 1
+            seed = (int(cfg.jitter_seed) << 32) | (self._jitter_calls & 0xffffffff)
+            self._last_jitter = (near, far, float(jitter), seed)
+            q = native.sample_and_query(self.grid(), R, cfg.z_depth_dim, cfg.SR, cfg.K, int(self.kernel_size[0]),
+                                        float(self.radius_limit_np), origin=origin, dirs=dirs, want_stats=want_stats,
+                                        jitter_gen=self._last_jitter)
+            return q, origin, R_c2w, dirs
+        t = self.coarse_t(R, near, far, jitter, generator)     # torch path: jitter 0 (shared table) or an explicit generator
         q = native.sample_and_query(self.grid(), R, cfg.z_depth_dim, cfg.SR, cfg.K, int(self.kernel_size[0]),
                                     float(self.radius_limit_np), origin=origin, dirs=dirs, t_vals=t, want_stats=want_stats)
         return q, origin, R_c2w, dirs

@@ -115,10 +115,22 @@ class QueryResult:
     stats: Optional[torch.Tensor] = None   # (2,) u64 as int64: voxel entries visited, candidates examined
 
 
+def coarse_t(near: float, far: float, jitter: float, seed: int, R: int, D: int, device, want_u: bool = False):
+    """The (R,D) t mid-points (and uniforms) the jittered sample selection generates in registers -- checker hook."""
+    lib = _lib.load()
+    t = torch.empty((R, D), dtype=torch.float32, device=device)
+    u = torch.empty((R, D), dtype=torch.float32, device=device) if want_u else None
+    check(lib.pnerf_coarse_t(C.c_float(near), C.c_float(far), C.c_float(jitter), C.c_uint64(seed), R, D, _ptr(t), _ptr(u), _stream()),
+          "pnerf_coarse_t")
+    return (t, u) if want_u else t
+
+
 def sample_and_query(grid: VoxelGrid, R: int, D: int, SR: int, K: int, kernel_size0: int, radius: float,
                      raypos: Optional[torch.Tensor] = None, origin=None, dirs: Optional[torch.Tensor] = None,
-                     t_vals: Optional[torch.Tensor] = None, want_stats: bool = False) -> QueryResult:
-    """Rows G0/G2/Q: select the first SR occupied coarse positions per ray and query K neighbours each."""
+                     t_vals: Optional[torch.Tensor] = None, want_stats: bool = False, jitter_gen=None) -> QueryResult:
+    """Rows G0/G2/Q: select the first SR occupied coarse positions per ray and query K neighbours each.
+    Position source: `raypos` (R,D,3), or origin + dirs * `t_vals` ((D,) or (R,D)), or -- `jitter_gen` =
+    (near, far, jitter, seed) -- jittered t generated inside the selection kernel."""
     lib = _lib.load()
     dev = grid.cell_start.device
     loc = torch.empty((R, SR, 3), dtype=torch.float32, device=dev)
@@ -127,13 +139,19 @@ def sample_and_query(grid: VoxelGrid, R: int, D: int, SR: int, K: int, kernel_si
     valid = torch.empty((R, SR), dtype=torch.uint8, device=dev)
     stats = torch.zeros(2, dtype=torch.int64, device=dev) if want_stats else None
     t_stride = 0
-    if raypos is None:
+    if raypos is None and jitter_gen is None:
         assert dirs is not None and t_vals is not None and origin is not None
         t_stride = 0 if t_vals.dim() == 1 else D
     with Timers.span("select"):
-        check(lib.pnerf_sample_select(C.byref(grid.view), _ptr(raypos, torch.float32), _f3(origin) if origin is not None else None,
-                                      _ptr(dirs, torch.float32), _ptr(t_vals, torch.float32), t_stride, R, D, SR, _ptr(loc),
-                                      _ptr(cnt), _stream()), "pnerf_sample_select")
+        if jitter_gen is not None:
+            near, far, jitter, seed = jitter_gen
+            check(lib.pnerf_sample_select_jitter(C.byref(grid.view), _f3(origin), _ptr(dirs, torch.float32), C.c_float(near),
+                                                 C.c_float(far), C.c_float(jitter), C.c_uint64(int(seed)), R, D, SR, _ptr(loc),
+                                                 _ptr(cnt), _stream()), "pnerf_sample_select_jitter")
+        else:
+            check(lib.pnerf_sample_select(C.byref(grid.view), _ptr(raypos, torch.float32), _f3(origin) if origin is not None else None,
+                                          _ptr(dirs, torch.float32), _ptr(t_vals, torch.float32), t_stride, R, D, SR, _ptr(loc),
+                                          _ptr(cnt), _stream()), "pnerf_sample_select")
     with Timers.span("query"):
         check(lib.pnerf_query(C.byref(grid.view), _ptr(loc), _ptr(cnt), R, SR, K, int(kernel_size0), C.c_float(float(radius)),
                               _ptr(pidx), _ptr(valid), _ptr(stats), _stream()), "pnerf_query")

@@ -269,3 +269,43 @@ def test_eval_mode_clamps_and_chunks():
     assert a["coarse_raycolor"].shape == (len(pix), 3)
     torch.testing.assert_close(a["coarse_raycolor"], b["coarse_raycolor"], rtol=0, atol=0)
     assert float(a["coarse_raycolor"].min()) >= 0 and float(a["coarse_raycolor"].max()) <= 1
+
+
+def test_in_kernel_jitter_replays_through_t_table():
+    """The jittered selection generates its t mid-points in registers (Philox); pnerf_coarse_t exposes the same table.
+    (a) the table follows RM:312-329 evaluated in float64 on the same uniforms, (b) the uniforms are uniform and differ
+    between rays / seeds, (c) selecting through the t-table source with that table gives bit-identical samples, and the
+    oracle querier on those positions gives the same neighbours."""
+    from pointnerf2studio_b200 import native
+    s, cloud, cam, pix = _scene("config1")
+    xyz = _cuda(cloud.xyz)
+    frame = native.get_hyperparameters(xyz, [0.004] * 3, [2, 2, 2], [3, 3, 3], RANGES)
+    grid = native.VoxelGrid(xyz, frame, s["P"], [3, 3, 3])
+    R, D = len(pix), 400
+    near, far, jitter, seed = cam.near, cam.far, 0.3, (7 << 32) | 5
+    t, u = native.coarse_t(near, far, jitter, seed, R, D, xyz.device, want_u=True)
+    t2 = native.coarse_t(near, far, jitter, seed + 1, R, D, xyz.device)
+    tn, un = t.cpu().numpy().astype(np.float64), u.cpu().numpy().astype(np.float64)
+    assert un.min() >= 0.0 and un.max() < 1.0
+    assert abs(un.mean() - 0.5) < 5e-3 and abs(un.var() - 1 / 12) < 2e-3
+    hist = np.histogram(un, bins=16, range=(0, 1))[0] / un.size
+    assert np.abs(hist - 1 / 16).max() < 3e-3
+    assert abs(np.corrcoef(un[0], un[1])[0, 1]) < 0.2 and not np.array_equal(t.cpu().numpy(), t2.cpu().numpy())
+    edge = near * (1 - np.linspace(0, 1, D + 1)) + far * np.linspace(0, 1, D + 1)
+    seg = np.diff(edge)[None] * (1 + jitter * (un - 0.5))
+    end = near + np.concatenate([np.zeros((R, 1)), np.cumsum(seg, 1)], 1)
+    np.testing.assert_allclose(tn, 0.5 * (end[:, :-1] + end[:, 1:]), rtol=0, atol=2e-5)
+    dirs = _cuda(cam.rays(pix))
+    qa = native.sample_and_query(grid, R, D, s["SR"], s["K"], 3, 0.016, origin=cam.origin, dirs=dirs,
+                                 jitter_gen=(near, far, jitter, seed))
+    qb = native.sample_and_query(grid, R, D, s["SR"], s["K"], 3, 0.016, origin=cam.origin, dirs=dirs, t_vals=t)
+    torch.cuda.synchronize()
+    for a, b in ((qa.sample_loc, qb.sample_loc), (qa.sample_cnt, qb.sample_cnt), (qa.sample_pidx, qb.sample_pidx)):
+        np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+    raypos = (torch.from_numpy(cam.origin)[None, None] + torch.from_numpy(cam.rays(pix))[:, None] * t.cpu()[..., None]).numpy()
+    frame_o = gq.hyperparameters(cloud.xyz, [0.004] * 3, [2, 2, 2], [3, 3, 3], RANGES)
+    pidx_o, loc_o, mask_o, hit_o = query_c.woord_query_grid_point_index(raypos, cloud.xyz, [3, 3, 3], [3, 3, 3], s["SR"], s["K"],
+                                                                        frame_o, s["P"], np.float32(0.016))
+    np.testing.assert_array_equal(qa.sample_loc.cpu().numpy(), loc_o)
+    np.testing.assert_array_equal(qa.sample_pidx.cpu().numpy(), pidx_o)
+    assert int(qa.sample_cnt.sum()) > 1000
