@@ -190,6 +190,11 @@ int pnerf_field_forward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h,
                            const int* sample_ids, int n_samples, int SR, int K, float* sigma, float* rgb, void* workspace,
                            int64_t workspace_bytes, void* stream);
 
+/* Profiling hook: when `buf` (device, pnerf_tc_trace_bytes() bytes, zero-filled) is set, CTA 0 of the next field_tc launches
+ * appends clock64-stamped pipeline events per role warp (tools/tc_trace.py decodes them).  NULL switches it off. */
+int pnerf_tc_set_trace(void* buf);
+int64_t pnerf_tc_trace_bytes(void);
+
 /* ---------------------------------------------------------------- step length + compositing (rows D, C, F)
  * Replaces SM:368-390 (+ nerfstudio RGBRenderer) and fill_invalid SM:491-504; original-flow twin
  * NPV:271-279 + ray_march RM:495-541.  One warp per ray, all R rays (missed rays -> bg).
@@ -212,6 +217,11 @@ int pnerf_conf_loss(const float* conf, const int* sample_pidx, const int8_t* ray
  * D[128xN] = A[128xK] * W[NxK]^T (bf16 in, fp32 out) through tcgen05.mma / TMEM / bulk async copy.
  * A: bf16 row major; Wp: bf16 in the K-slab layout [K/8][N][8] (see csrc/umma.cuh). */
 int pnerf_umma_selftest(const void* A, const void* Wp, float* D, int N, int K, void* stream);
+
+/* Micro-benchmarks of the resources the tensor-core kernels lean on (one CTA per SM, all SMs): which = 0 tcgen05.mma
+ * rate (param = N), 1 L2 -> shared bulk-copy ring (param = chunk bytes, src >= 557056 bytes), 2 tcgen05.ld rate
+ * (param = warps).  out[148] = cycles for `iters` operations per CTA. */
+int pnerf_tc_microbench(int which, int iters, int param, const void* src, unsigned long long* out, float* sink, void* stream);
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,8 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(MlpGrad), C.c_void_p, C.c_int64, C.c_void_p]),
+    "pnerf_tc_set_trace": (C.c_int, [C.c_void_p]),
+    "pnerf_tc_trace_bytes": (C.c_int64, []),
     "pnerf_tc_wpack_bytes": (C.c_int64, []),
     "pnerf_tc_pack_weights": (C.c_int, [C.POINTER(Mlp), C.c_void_p, C.c_void_p]),
     "pnerf_field_tc_workspace_bytes": (C.c_int64, [C.c_int64]),
@@ -96,6 +98,7 @@ SIGNATURES = {
     "pnerf_composite_backward": (C.c_int, [C.POINTER(Camera), C.POINTER(Mode), C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pnerf_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "pnerf_tc_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pnerf_conf_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
 }

@@ -4,20 +4,26 @@
 // (twin PA:486-662,745-830); the reference runs the same math as ~40 separate torch/cuBLAS launches with every
 // (M,256) fp32 activation round-tripping HBM.
 //
-// field_tc_kernel -- one CTA per SM, 448 threads, two tile slots in ping-pong:
+// field_tc_kernel -- CTA PAIRS (cluster of 2 = the two SMs of a TPC, tcgen05 cta_group::2), one CTA per SM, 448 threads,
+// two tile slots in ping-pong.  One MMA (M = 256, N = 256, K = 16) spans the pair: each CTA supplies its own 128 rows
+// of A and only HALF of every weight chunk (its 128 of the 256 output features), so the L2 -> SM weight stream -- the
+// bound of the single-CTA version (557 KB per 128-row tile against ~43 B/clk/SM of L2) -- is halved per SM.
 //   tile      = 128 rows = (128/KP) consecutive valid samples x KP neighbour slots (KP = 8, 16 or 32 >= K)
 //   warps 0-3 : encoder.  Thread = row: gathers the point (xyz, 32-d embedding, colour, dir, conf), computes the
 //               relative position in world and perspective space, the inverse-distance weight, the 284-wide encoded
 //               input (double-angle recurrences from one sincos per input) and writes it as the bf16 A operand of
 //               layer 1 straight into shared memory (K-slab layout, see umma.cuh).  Nothing encoded touches HBM.
-//   warps 4-7 / 8-11 : epilogue group of slot 0 / 1.  Thread = row = TMEM lane: tcgen05.ld the fp32 accumulator,
-//               bias + LeakyReLU, bf16 pack, write the next layer's A operand in place; after layer 4 the density
-//               head (in-thread dot), the weight w_k and the sum over the KP neighbour lanes (register butterfly).
-//   warp 12   : weight producer: streams the four 256-wide layers (bf16, pre-packed K-slabs, L2 resident) as
-//               16 KB chunks through a 4-stage ring with cp.async.bulk + mbarrier complete_tx.
-//   warp 13   : MMA issuer: one thread issues tcgen05.mma (M=128, N=256, K=16) for slot 0 / slot 1 alternately,
-//               so one slot's epilogue overlaps the other slot's MMAs; tcgen05.commit releases ring stages
-//               and publishes accumulators.
+//   warps 4-11 / 12-19 : epilogue group of slot 0 / 1, two warps per 32 TMEM lanes (one per 128-column half: the roles
+//               are latency-bound, so a second warp per lane quarter nearly halves an epilogue).  Thread = row = TMEM
+//               lane: tcgen05.ld the fp32 accumulator, bias + LeakyReLU, bf16 pack, write the next layer's A operand in
+//               place; after layer 4 the density head (in-thread dot, halves combined through shared memory), the
+//               weight w_k and the sum over the KP neighbour lanes (register butterfly).
+//   warp 20   : weight producer: streams this CTA's half of the four 256-wide layers (bf16, pre-packed K-slabs, L2
+//               resident) as 8 KB half-chunks through an 8-stage ring with cp.async.bulk + mbarrier complete_tx.
+//   warp 21   : leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 for slot 0 / slot 1 alternately,
+//               so one slot's epilogue overlaps the other slot's MMAs; multicast tcgen05.commit releases ring stages
+//               and publishes accumulators in both CTAs.  Peer CTA: relay -- forwards "my half-chunk has landed" to
+//               the leader.  Barriers the issuer waits on live in the leader (remote arrivals from the peer).
 //   TMEM      : 512 columns = 2 slots x (128 lanes x 256 fp32 columns).
 //   HBM       : in 168 B per valid row (gather) + indices; out 4 B sigma + 512 B F_s (bf16) per sample.
 #include "pnerf_common.cuh"
@@ -32,38 +38,45 @@ constexpr int ROWS = 128;
 constexpr int SLAB = ROWS * 16;                  // bytes of one 8-wide k-slab of a 128-row operand
 constexpr int KIN_PAD = 288;                     // 284 (layer 1) and 263 (layer 3) padded to 9 chunks of 32
 constexpr int A_BYTES = (KIN_PAD / 8) * SLAB;    // 73728
-constexpr int CHUNK_K = 32;
-constexpr int CHUNK_BYTES = CHUNK_K * HID * 2;   // 16384: 4 slabs of a 256-row operand
-constexpr int NST = 4;
-constexpr int N_CHUNKS = 34;                     // 9 + 8 + 9 + 8
-constexpr int NT = 448;
+// Weight stream.  A bulk copy costs ~240 clk of engine time per SM whatever its size (measured, tools/tc_microbench.py:
+// 4, 8 and 16 KB copies all run at one per 235-245 clk with two issuing lanes, one per ~420 clk with a single lane), so
+// the stream is sized in few, large copies: a chunk is 64 k-columns of a layer, stored as two N-halves of 16 KB (one per
+// CTA of the pair); the 288-wide layers end with a half-size chunk (32 k-columns, 8 KB per CTA).
+constexpr int CHUNK_K = 64;
+constexpr int CHUNK_BYTES = CHUNK_K * HID * 2;   // 32768 for the pair
+constexpr int HALF_BYTES = CHUNK_BYTES / 2;      // 16384: what one CTA loads per full chunk: 8 slabs x 128 output features
+constexpr int N_UNITS = 34;                      // 32-k units of 16 KB in the packed buffer: 9 + 8 + 9 + 8
+constexpr int NT = 704;                          // 4 encoder + 2 x 8 epilogue + producer + issuer warps
 constexpr int MAX_SPT = 16;                      // samples per tile at KP = 8
 
 // colour network
 constexpr int HC = 128;
 constexpr int C1_BYTES = (KIN_PAD / 8) * HC * 16;   // 73728: Wc1 128 x 288
 constexpr int C2_BYTES = (HC / 8) * HC * 16;        // 32768: Wc2 / Wc3 128 x 128
-constexpr int WPACK_FIELD_BYTES = N_CHUNKS * CHUNK_BYTES;                  // 557056
+constexpr int WPACK_FIELD_BYTES = N_UNITS * 16384;                         // 557056
 constexpr int WPACK_BYTES = WPACK_FIELD_BYTES + C1_BYTES + 2 * C2_BYTES;   // 696320
 
 struct Cam { float o[3]; float Rc[9]; float Rw[9]; };
 
 struct Meta {                       // per (slot, tile parity): written by the encoder, read by the slot's epilogue group
     float w[ROWS];                  // aggregation weight of the row (0 for masked rows)
+    float dot_hi[ROWS];             // density-head partial dot of columns 128..255 (upper-half epilogue warp -> lower-half warp)
     uint4 extras[ROWS];             // bf16 x 8: colour 3, dir_r - v 3, <dir_r, v> 1, 0   (layer 3 inputs 256..263)
     int slot_id[MAX_SPT];           // output slot (r*SR+s) of each sample of the tile, -1 past the end
 };
 
 struct Smem {
     uint8_t A[2][A_BYTES];
-    uint8_t W[NST][CHUNK_BYTES];
+    uint8_t W[2][2][HALF_BYTES];        // two groups in flight, a group = up to two 64-k chunks (this CTA's N-half)
     float bias[4][HID];
     float wa[HID];
     Meta meta[2][2];
-    uint64_t w_full[NST], w_empty[NST];
+    uint64_t w_full[2], w_empty[2], w_peer[2];
     uint64_t a_ready[2], acc_full[2], acc_empty[2], a_free[2];
     uint32_t tmem_base;
 };
+
+static_assert(sizeof(Smem) <= 232448, "field_tc_kernel shared memory exceeds the 227 KB per-CTA limit");
 
 struct FieldParams {
     const float *xyz, *embed, *color, *dir, *conf;
@@ -77,6 +90,15 @@ struct FieldParams {
     int softplus, weight_conf;
     float* sigma;                   // (R*SR) by slot
     __nv_bfloat16* F;               // (S, 256) aggregated features, by compact sample index
+    unsigned long long* trace;      // profiling hook (pnerf_tc_set_trace): per-warp event timelines of CTA 0, or NULL
+};
+
+// Pipeline trace: lane 0 of a role warp of CTA 0 appends (clock64 << 8 | event) to its own 2048-entry lane of the buffer.
+constexpr int TRACE_PER_WARP = 2048;
+struct Tracer {
+    unsigned long long* buf; int n;
+    __device__ __forceinline__ Tracer(unsigned long long* b, int warp, int lane) : buf(b && blockIdx.x == 0 && lane == 0 ? b + warp * TRACE_PER_WARP : nullptr), n(1) {}
+    __device__ __forceinline__ void ev(int id) { if (buf && n < TRACE_PER_WARP) { buf[n++] = ((unsigned long long)clock64() << 8) | (unsigned)id; buf[0] = n; } }
 };
 
 __device__ __forceinline__ uint4 pack8(const float* v) {
@@ -112,16 +134,31 @@ __device__ __forceinline__ void pe(float x, float* out) {
 }
 
 // ---------------------------------------------------------------------------------------------- encoder
+// The gather is a three-level dependent chain (sample id -> neighbour index -> point row).  The encoder runs it two tiles
+// ahead: ids of tile j+2 are loaded and the point rows of tile j+1 are prefetched into L2 while tile j is encoded.
 template <int KP>
-__device__ __forceinline__ void encode_tile(const FieldParams& p, int tile, uint8_t* Abuf, Meta& meta, int row) {
+__device__ __forceinline__ void load_ids(const FieldParams& p, int tile, int row, int& slot, int& pidx) {
     constexpr int SPT = ROWS / KP;
     const int si = tile * SPT + row / KP;
     const int k = row % KP;
-    int slot = -1, pidx = -1;
+    slot = -1; pidx = -1;
     if (si < p.S) {
         slot = __ldg(p.sample_ids + si);
         if (k < p.K) pidx = __ldg(p.sample_pidx + (int64_t)slot * p.K + k);
     }
+}
+__device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+__device__ __forceinline__ void prefetch_point(const FieldParams& p, int pidx) {
+    if (pidx < 0) return;
+    prefetch_l2(p.embed + (int64_t)pidx * 32);
+    prefetch_l2(p.xyz + 3 * (int64_t)pidx);
+    prefetch_l2(p.color + 3 * (int64_t)pidx);
+    prefetch_l2(p.dir + 3 * (int64_t)pidx);
+}
+
+template <int KP>
+__device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int pidx, uint8_t* Abuf, Meta& meta, int row) {
+    const int k = row % KP;
     if (k == 0) meta.slot_id[row / KP] = slot;
     uint4* Arow = reinterpret_cast<uint4*>(Abuf + row * 16);   // slab j of this row = Arow[j * (SLAB/16)]
     constexpr int SJ = SLAB / 16;
@@ -194,27 +231,39 @@ __device__ __forceinline__ void encode_tile(const FieldParams& p, int tile, uint
 }
 
 // ---------------------------------------------------------------------------------------------- epilogues
-__device__ __forceinline__ void epilogue_store(uint32_t tacc_lane, const float* __restrict__ bias, float slope, uint8_t* Abuf,
-                                               int row) {
-    uint4* Arow = reinterpret_cast<uint4*>(Abuf + row * 16);
+// Hidden-layer epilogue of one 128-column half: bias + LeakyReLU in fp32, bf16 pack, next layer's A operand in place.
+// tcgen05.ld takes ~210 clk while the tensor pipe works on the other slot (60 clk idle; tools/tc_microbench.py), so the load
+// of chunk i+1 is issued before chunk i is processed (tcgen05.wait::ld waits for every outstanding load, hence the order).
+__device__ __forceinline__ void epilogue_chunk_store(float (&v)[32], const float* __restrict__ bias, float slope, uint4* Arow, int c0) {
     constexpr int SJ = SLAB / 16;
-#pragma unroll 1
-    for (int c0 = 0; c0 < HID; c0 += 32) {
-        float v[32];
-        tmem_ld32(tacc_lane + c0, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
-            float x;
-            x = v[j] + b.x; v[j] = fmaxf(x, x * slope);
-            x = v[j + 1] + b.y; v[j + 1] = fmaxf(x, x * slope);
-            x = v[j + 2] + b.z; v[j + 2] = fmaxf(x, x * slope);
-            x = v[j + 3] + b.w; v[j + 3] = fmaxf(x, x * slope);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) Arow[(c0 / 8 + j) * SJ] = pack8(v + 8 * j);
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
+        float x;
+        x = v[j] + b.x; v[j] = fmaxf(x, x * slope);
+        x = v[j + 1] + b.y; v[j + 1] = fmaxf(x, x * slope);
+        x = v[j + 2] + b.z; v[j + 2] = fmaxf(x, x * slope);
+        x = v[j + 3] + b.w; v[j + 3] = fmaxf(x, x * slope);
     }
+#pragma unroll
+    for (int j = 0; j < 4; j++) Arow[(c0 / 8 + j) * SJ] = pack8(v + 8 * j);
+}
+__device__ __forceinline__ void epilogue_store(uint32_t tacc_lane, const float* __restrict__ bias, float slope, uint8_t* Abuf,
+                                               int row, int cbeg) {
+    uint4* Arow = reinterpret_cast<uint4*>(Abuf + row * 16);
+    float va[32], vb[32];
+    tmem_ld32(tacc_lane + cbeg, va);
+    tmem_ld_wait();
+    tmem_ld32(tacc_lane + cbeg + 32, vb);
+    epilogue_chunk_store(va, bias, slope, Arow, cbeg);
+    tmem_ld_wait();
+    tmem_ld32(tacc_lane + cbeg + 64, va);
+    epilogue_chunk_store(vb, bias, slope, Arow, cbeg + 32);
+    tmem_ld_wait();
+    tmem_ld32(tacc_lane + cbeg + 96, vb);
+    epilogue_chunk_store(va, bias, slope, Arow, cbeg + 64);
+    tmem_ld_wait();
+    epilogue_chunk_store(vb, bias, slope, Arow, cbeg + 96);
 }
 
 // sum over the KP lanes of a neighbour group of 32 per-lane values; afterwards lane gl (position in its group)
@@ -239,44 +288,63 @@ __device__ __forceinline__ void butterfly(float* a, int lane) {
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
 template <int KP>
+__device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)[32], const float* __restrict__ bias,
+                                                const float* __restrict__ wa, float w, float& dot, int slot, int si, int c0, int lane) {
+    constexpr int VPL = 32 / KP;
+    const int gl = lane % KP;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
+        const float4 a = *reinterpret_cast<const float4*>(wa + c0 + j);
+        float x;
+        x = v[j] + b.x; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.x, dot); v[j] = x * w;
+        x = v[j + 1] + b.y; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.y, dot); v[j + 1] = x * w;
+        x = v[j + 2] + b.z; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.z, dot); v[j + 2] = x * w;
+        x = v[j + 3] + b.w; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.w, dot); v[j + 3] = x * w;
+    }
+    butterfly<KP>(v, lane);
+    if (slot >= 0) {
+        __nv_bfloat16* dst = p.F + (int64_t)si * HID + c0 + gl * VPL;
+        if (VPL == 4) {
+            uint2 o; o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+            *reinterpret_cast<uint2*>(dst) = o;
+        } else if (VPL == 2) {
+            *reinterpret_cast<uint32_t*>(dst) = pack_bf16(v[0], v[1]);
+        } else {
+            dst[0] = __float2bfloat16(v[0]);
+        }
+    }
+}
+
+template <int KP>
 __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_t tacc_lane, const float* __restrict__ bias,
-                                                   const float* __restrict__ wa, const Meta& meta, int tile, int row) {
-    constexpr int SPT = ROWS / KP, VPL = 32 / KP;
+                                                   const float* __restrict__ wa, Meta& meta, int tile, int row, int half, int bar_id) {
+    constexpr int SPT = ROWS / KP;
     const int lane = threadIdx.x & 31, gl = lane % KP;
     const int sl = row / KP;
     const int si = tile * SPT + sl;
     const float w = meta.w[row];
     const int slot = meta.slot_id[sl];
     float dot = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < HID; c0 += 32) {
-        float v[32];
-        tmem_ld32(tacc_lane + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
-            const float4 a = *reinterpret_cast<const float4*>(wa + c0 + j);
-            float x;
-            x = v[j] + b.x; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.x, dot); v[j] = x * w;
-            x = v[j + 1] + b.y; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.y, dot); v[j + 1] = x * w;
-            x = v[j + 2] + b.z; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.z, dot); v[j + 2] = x * w;
-            x = v[j + 3] + b.w; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.w, dot); v[j + 3] = x * w;
-        }
-        butterfly<KP>(v, lane);
-        if (slot >= 0) {
-            __nv_bfloat16* dst = p.F + (int64_t)si * HID + c0 + gl * VPL;
-            if (VPL == 4) {
-                uint2 o; o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-                *reinterpret_cast<uint2*>(dst) = o;
-            } else if (VPL == 2) {
-                *reinterpret_cast<uint32_t*>(dst) = pack_bf16(v[0], v[1]);
-            } else {
-                dst[0] = __float2bfloat16(v[0]);
-            }
-        }
-    }
-    const float raw = dot + __ldg(p.ba);
+    const int cbeg = half * (HID / 2);
+    float va[32], vb[32];
+    tmem_ld32(tacc_lane + cbeg, va);
+    tmem_ld_wait();
+    tmem_ld32(tacc_lane + cbeg + 32, vb);
+    aggregate_chunk<KP>(p, va, bias, wa, w, dot, slot, si, cbeg, lane);
+    tmem_ld_wait();
+    tmem_ld32(tacc_lane + cbeg + 64, va);
+    aggregate_chunk<KP>(p, vb, bias, wa, w, dot, slot, si, cbeg + 32, lane);
+    tmem_ld_wait();
+    tmem_ld32(tacc_lane + cbeg + 96, vb);
+    aggregate_chunk<KP>(p, va, bias, wa, w, dot, slot, si, cbeg + 64, lane);
+    tmem_ld_wait();
+    aggregate_chunk<KP>(p, vb, bias, wa, w, dot, slot, si, cbeg + 96, lane);
+    // combine the two column halves of the density head: the upper-half warp hands its partial dot to the lower-half warp
+    if (half) meta.dot_hi[row] = dot;
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    if (half) return;
+    const float raw = dot + meta.dot_hi[row] + __ldg(p.ba);
     const float a = p.softplus ? softplus_f(raw - 1.f) : fmaxf(raw, 0.f);   // PA:260-265 / SM:221
     float sg = w * a;
 #pragma unroll
@@ -284,58 +352,93 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
     if (gl == 0 && slot >= 0) p.sigma[slot] = sg;                           // SM:344
 }
 
-__host__ __device__ constexpr int layer_chunks(int L) { return (L & 1) ? 8 : 9; }
-__host__ __device__ constexpr int layer_chunk0(int L) { return L == 0 ? 0 : (L == 1 ? 9 : (L == 2 ? 17 : 26)); }
+__host__ __device__ constexpr int layer_slabs(int L) { return (L & 1) ? 32 : 36; }     // 8-wide k-slabs of the layer (K = 256 / 288)
+__host__ __device__ constexpr int layer_chunks(int L) { return (L & 1) ? 4 : 5; }      // 64-k chunks, the last of a 288 layer is half
+__host__ __device__ constexpr int layer_byte0(int L) { return 16384 * (L == 0 ? 0 : (L == 1 ? 9 : (L == 2 ? 17 : 26))); }
+__host__ __device__ constexpr int chunk_slabs(int L, int c) { return layer_slabs(L) - 8 * c < 8 ? layer_slabs(L) - 8 * c : 8; }
+
+// The order in which (slot, layer) steps go through the tensor pipe, shared by the weight producer, the MMA issuer and the
+// relay.  Slot s works on this CTA's tiles j = 2*it + s; step q of a slot is layer q & 3 of its tile q >> 2.  Slot 1 runs
+// two layers behind slot 0, so the encoder has two layer-times of the other slot's MMAs to refill a slot's A buffer.
+template <class F>
+__device__ __forceinline__ void for_each_step(int n_my, F&& fn) {
+    const int n0 = 4 * ((n_my + 1) >> 1), n1 = 4 * (n_my >> 1);
+    const int n = n0 > n1 + 2 ? n0 : n1 + 2;
+    for (int a = 0; a < n; a++) {
+        if (a >= 2 && a - 2 < n1) fn(1, (a - 2) & 3, (a - 2) >> 2);
+        if (a < n0) fn(0, a & 3, a >> 2);
+    }
+}
 
 template <int KP>
-__global__ void __launch_bounds__(NT, 1) field_tc_kernel(const FieldParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kernel(const FieldParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_my = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t rank = cluster_ctarank();                      // 0 = leader (issues the MMAs)
+    const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
+    const int n_super = (p.n_tiles + 1) >> 1;                     // 256-row super-tiles; this CTA takes tile 2*T + rank
+    const int n_my = n_super > pair ? (n_super - pair + n_pairs - 1) / n_pairs : 0;
+    auto tile_of = [&](int j) { return 2 * (pair + j * n_pairs) + (int)rank; };
 
     if (tid == 0) {
-        for (int i = 0; i < NST; i++) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); mbar_init(&sm.w_peer[i], 1); }
         for (int s = 0; s < 2; s++) {
-            mbar_init(&sm.a_ready[s], 128); mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.acc_empty[s], 128); mbar_init(&sm.a_free[s], 1);
+            // a_ready / acc_empty: one arrival per epilogue warp of the pair (2 CTAs x 8); the 4 encoder warps arrive twice
+            mbar_init(&sm.a_ready[s], 16); mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.acc_empty[s], 16); mbar_init(&sm.a_free[s], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 13) tmem_alloc(&sm.tmem_base, 512);
+    if (warp == 21) tmem_alloc2(&sm.tmem_base, 512);
     for (int i = tid; i < HID; i += NT) {
         sm.bias[0][i] = p.b1[i]; sm.bias[1][i] = p.b2[i]; sm.bias[2][i] = p.b3[i]; sm.bias[3][i] = p.b4[i];
         sm.wa[i] = p.wa[i];
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();          // both CTAs' barriers exist before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
+    Tracer tr(p.trace, warp, lane);
     if (warp < 4) {
         // ===================================================== encoder
         uint32_t ph[2] = {0, 0};
+        int slot0, pidx0, slot1 = -1, pidx1 = -1;
+        load_ids<KP>(p, tile_of(0), tid, slot0, pidx0);
+        if (n_my > 1) load_ids<KP>(p, tile_of(1), tid, slot1, pidx1);
         for (int j = 0; j < n_my; j++) {
             const int s = j & 1;
+            int slot2 = -1, pidx2 = -1;
+            if (j + 2 < n_my) load_ids<KP>(p, tile_of(j + 2), tid, slot2, pidx2);
+            prefetch_point(p, pidx1);
             if (j >= 2) { mbar_wait(&sm.a_free[s], ph[s]); ph[s] ^= 1; }
-            encode_tile<KP>(p, (int)blockIdx.x + j * (int)gridDim.x, sm.A[s], sm.meta[s][(j >> 1) & 1], tid);
+            tr.ev(1);
+            encode_tile<KP>(p, slot0, pidx0, sm.A[s], sm.meta[s][(j >> 1) & 1], tid);
+            slot0 = slot1; pidx0 = pidx1; slot1 = slot2; pidx1 = pidx2;
             fence_proxy_async();
-            mbar_arrive(&sm.a_ready[s]);
+            __syncwarp();
+            if (lane == 0) { mbar_arrive_remote(&sm.a_ready[s], 0); mbar_arrive_remote(&sm.a_ready[s], 0); }
+            tr.ev(2);
         }
-    } else if (warp < 12) {
-        // ===================================================== epilogue group of slot s
-        const int s = (warp - 4) >> 2;
-        const int row = tid - 128 - s * 128;
+    } else if (warp < 20) {
+        // ===================================================== epilogue group of slot s: warp = lane quarter (warp & 3, the
+        // TMEM lanes a warp may touch) x column half
+        const int s = (warp - 4) >> 3;
+        const int half = ((warp - 4) >> 2) & 1;
+        const int row = (warp & 3) * 32 + lane;
         const uint32_t tacc_lane = tmem + (uint32_t)(s * HID) + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t ph = 0;
         for (int j = s; j < n_my; j += 2) {
-            const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+            const int tile = tile_of(j);
             Meta& meta = sm.meta[s][(j >> 1) & 1];
 #pragma unroll 1
             for (int L = 0; L < 3; L++) {
                 mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
                 tc_fence_after();
-                epilogue_store(tacc_lane, sm.bias[L], p.slope, sm.A[s], row);
-                if (L == 1) {   // layer-3 input columns 256..287: the 7 per-row extras, then zeros
+                tr.ev(10 + L);
+                epilogue_store(tacc_lane, sm.bias[L], p.slope, sm.A[s], row, half * (HID / 2));
+                if (L == 1 && half) {   // layer-3 input columns 256..287: the 7 per-row extras, then zeros
                     uint4* Arow = reinterpret_cast<uint4*>(sm.A[s] + row * 16);
                     Arow[32 * (SLAB / 16)] = meta.extras[row];
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -343,62 +446,96 @@ __global__ void __launch_bounds__(NT, 1) field_tc_kernel(const FieldParams p) {
                 }
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(&sm.a_ready[s]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&sm.a_ready[s], 0);
+                tr.ev(20 + L);
             }
             mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
             tc_fence_after();
-            epilogue_aggregate<KP>(p, tacc_lane, sm.bias[3], sm.wa, meta, tile, row);
+            tr.ev(13);
+            epilogue_aggregate<KP>(p, tacc_lane, sm.bias[3], sm.wa, meta, tile, row, half, 1 + s * 4 + (warp & 3));
             tc_fence_before();
-            mbar_arrive(&sm.acc_empty[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&sm.acc_empty[s], 0);
+            tr.ev(23);
         }
-    } else if (warp == 12) {
+    } else if (warp == 20) {
         // ===================================================== weight producer
+        // Two issuing lanes (one lane alone sustains only a copy per ~420 clk): lane e loads chunk e of every group.
+        if (lane < 2) {
+            uint32_t g = 0;
+            for_each_step(n_my, [&](int s, int L, int it) {
+                (void)s; (void)it;
+                for (int c0 = 0; c0 < layer_chunks(L); c0 += 2, g++) {
+                    const uint32_t b = g & 1, phase = (g >> 1) & 1;
+                    const int nc = layer_chunks(L) - c0 < 2 ? 1 : 2;
+                    mbar_wait(&sm.w_empty[b], phase ^ 1);
+                    if (lane == 0) {
+                        uint32_t total = 0;
+                        for (int e = 0; e < nc; e++) total += (uint32_t)chunk_slabs(L, c0 + e) * 2048u;
+                        mbar_arrive_expect_tx(&sm.w_full[b], total);
+                    }
+                    if (lane < nc) {
+                        const int c = c0 + lane;
+                        const uint32_t bytes = (uint32_t)chunk_slabs(L, c) * 2048u;            // this CTA's N-half of the chunk
+                        bulk_g2s(sm.W[b][lane], p.wpack + layer_byte0(L) + (size_t)c * CHUNK_BYTES + rank * bytes, bytes, &sm.w_full[b]);
+                    }
+                }
+            });
+        }
+    } else if (rank == 0) {
+        // ===================================================== MMA issuer (leader CTA only)
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int j0 = 0; j0 < n_my; j0 += 2)
-                for (int L = 0; L < 4; L++)
-                    for (int s = 0; s < 2 && j0 + s < n_my; s++)
-                        for (int c = 0; c < layer_chunks(L); c++) {
-                            mbar_wait(&sm.w_empty[stage], phase ^ 1);
-                            mbar_arrive_expect_tx(&sm.w_full[stage], CHUNK_BYTES);
-                            bulk_g2s(sm.W[stage], p.wpack + (size_t)(layer_chunk0(L) + c) * CHUNK_BYTES, CHUNK_BYTES, &sm.w_full[stage]);
-                            if (++stage == NST) { stage = 0; phase ^= 1; }
+            const uint32_t idesc = make_idesc_bf16(2 * ROWS, HID);
+            uint32_t g = 0, ar[2] = {0, 0}, ae[2] = {0, 0};
+            for_each_step(n_my, [&](int s, int L, int it) {
+                tr.ev(30 + 4 * s + L);
+                mbar_wait_cluster(&sm.a_ready[s], ar[s]); ar[s] ^= 1;
+                if (L == 0 && it >= 1) { mbar_wait_cluster(&sm.acc_empty[s], ae[s]); ae[s] ^= 1; }
+                tc_fence_after();
+                tr.ev(40 + 4 * s + L);
+                const uint32_t tacc = tmem + (uint32_t)(s * HID);
+                const uint32_t a_base = smem_u32(sm.A[s]);
+                for (int c0 = 0; c0 < layer_chunks(L); c0 += 2, g++) {
+                    const uint32_t b = g & 1, phase = (g >> 1) & 1;
+                    const int nc = layer_chunks(L) - c0 < 2 ? 1 : 2;
+                    mbar_wait(&sm.w_full[b], phase);
+                    mbar_wait_cluster(&sm.w_peer[b], phase);
+                    tc_fence_after();
+                    for (int e = 0; e < nc; e++) {
+                        const int c = c0 + e;
+                        const uint32_t b_base = smem_u32(sm.W[b][e]);
+                        const int nk = chunk_slabs(L, c) >> 1;
+                        for (int kk = 0; kk < nk; kk++) {
+                            const uint64_t ad = make_smem_desc(a_base + (uint32_t)((c * 8 + kk * 2) * SLAB), SLAB, 128);
+                            const uint64_t bd = make_smem_desc(b_base + (uint32_t)(kk * 2 * (HID / 2) * 16), (HID / 2) * 16, 128);
+                            mma_bf16_2cta(tacc, ad, bd, idesc, (uint32_t)((c | kk) > 0));
                         }
+                    }
+                    mma_commit2(&sm.w_empty[b], 3);     // one commit per group: a tcgen05.commit costs ~120 clk of MMA time
+                }
+                mma_commit2(&sm.acc_full[s], 3);
+                if (L == 3) mma_commit2(&sm.a_free[s], 3);
+                tr.ev(50 + 4 * s + L);
+            });
         }
     } else {
-        // ===================================================== MMA issuer
+        // ===================================================== relay (peer CTA): my half of the group landed -> tell the leader
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(ROWS, HID);
-            uint32_t stage = 0, phase = 0, ar[2] = {0, 0}, ae[2] = {0, 0};
-            for (int j0 = 0; j0 < n_my; j0 += 2)
-                for (int L = 0; L < 4; L++)
-                    for (int s = 0; s < 2 && j0 + s < n_my; s++) {
-                        mbar_wait(&sm.a_ready[s], ar[s]); ar[s] ^= 1;
-                        if (L == 0 && j0 >= 2) { mbar_wait(&sm.acc_empty[s], ae[s]); ae[s] ^= 1; }
-                        tc_fence_after();
-                        const uint32_t tacc = tmem + (uint32_t)(s * HID);
-                        const uint32_t a_base = smem_u32(sm.A[s]);
-                        for (int c = 0; c < layer_chunks(L); c++) {
-                            mbar_wait(&sm.w_full[stage], phase);
-                            tc_fence_after();
-                            const uint32_t b_base = smem_u32(sm.W[stage]);
-#pragma unroll
-                            for (int kk = 0; kk < 2; kk++) {
-                                const uint64_t ad = make_smem_desc(a_base + (uint32_t)((c * 4 + kk * 2) * SLAB), SLAB, 128);
-                                const uint64_t bd = make_smem_desc(b_base + (uint32_t)(kk * 2 * HID * 16), HID * 16, 128);
-                                mma_bf16(tacc, ad, bd, idesc, (uint32_t)((c | kk) > 0));
-                            }
-                            mma_commit(&sm.w_empty[stage]);
-                            if (++stage == NST) { stage = 0; phase ^= 1; }
-                        }
-                        mma_commit(&sm.acc_full[s]);
-                        if (L == 3) mma_commit(&sm.a_free[s]);
-                    }
+            uint32_t g = 0;
+            for_each_step(n_my, [&](int s, int L, int it) {
+                (void)s; (void)it;
+                for (int c0 = 0; c0 < layer_chunks(L); c0 += 2, g++) {
+                    mbar_wait(&sm.w_full[g & 1], (g >> 1) & 1);
+                    mbar_arrive_remote(&sm.w_peer[g & 1], 0);
+                }
+            });
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 13) tmem_dealloc(tmem, 512);
+    cluster_sync_all();          // nobody leaves while the peer may still signal it / the pair's MMAs are in flight
+    if (warp == 21) tmem_dealloc2(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------- colour network
@@ -550,7 +687,7 @@ __global__ void __launch_bounds__(128, 1) color_tc_kernel(const ColorParams p) {
 
 // ---------------------------------------------------------------------------------------------- weight packing
 // fp32 nn.Linear weights (out,in) -> bf16 K-slab layout [k/8][out][8], K zero-padded; 34 field chunks then Wc1, Wc2, Wc3.
-struct PackJob { const float* w; int out, in, kpad; int64_t dst_off; };
+struct PackJob { const float* w; int out, in, kpad; int64_t dst_off; int split; };
 struct PackJobs { PackJob j[7]; };
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(PackJobs jobs, uint8_t* __restrict__ dst) {
@@ -560,7 +697,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackJobs jobs, uint8_
         const int k = i % jb.kpad, n = i / jb.kpad;
         const float v = k < jb.in ? jb.w[(int64_t)n * jb.in + k] : 0.f;
         __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst + jb.dst_off);
-        d[((int64_t)(k >> 3) * jb.out + n) * 8 + (k & 7)] = __float2bfloat16(v);
+        if (jb.split) {   // field layers: 64-k chunks of [N-half 2][k-slab <=8][128 features][8]: a CTA of a pair bulk-copies one half
+            const int ks = k >> 3, h = n >> 7, c = ks >> 3;
+            const int nsl = jb.kpad / 8 - 8 * c < 8 ? jb.kpad / 8 - 8 * c : 8;
+            d[(int64_t)c * 16384 + ((int64_t)h * nsl + (ks & 7)) * 1024 + (n & 127) * 8 + (k & 7)] = __float2bfloat16(v);
+        } else {
+            d[((int64_t)(k >> 3) * jb.out + n) * 8 + (k & 7)] = __float2bfloat16(v);
+        }
     }
 }
 
@@ -576,18 +719,22 @@ Cam make_cam(const pnerf_points* pts, const pnerf_camera* cam) {
 
 using namespace pnerf;
 
+static unsigned long long* g_trace = nullptr;
+extern "C" int pnerf_tc_set_trace(void* buf) { g_trace = (unsigned long long*)buf; return PNERF_OK; }
+extern "C" int64_t pnerf_tc_trace_bytes(void) { return (int64_t)24 * TRACE_PER_WARP * 8; }
+
 extern "C" int64_t pnerf_tc_wpack_bytes(void) { return WPACK_BYTES; }
 
 extern "C" int pnerf_tc_pack_weights(const pnerf_mlp* mlp, void* wpack, void* stream) {
     if (!mlp || !wpack) return PNERF_ERR_ARG;
     PackJobs jobs;
-    jobs.j[0] = {mlp->w1, 256, 284, 288, 0};
-    jobs.j[1] = {mlp->w2, 256, 256, 256, (int64_t)9 * CHUNK_BYTES};
-    jobs.j[2] = {mlp->w3, 256, 263, 288, (int64_t)17 * CHUNK_BYTES};
-    jobs.j[3] = {mlp->w4, 256, 256, 256, (int64_t)26 * CHUNK_BYTES};
-    jobs.j[4] = {mlp->wc1, 128, 280, 288, (int64_t)WPACK_FIELD_BYTES};
-    jobs.j[5] = {mlp->wc2, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES};
-    jobs.j[6] = {mlp->wc3, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES + C2_BYTES};
+    jobs.j[0] = {mlp->w1, 256, 284, 288, 0, 1};
+    jobs.j[1] = {mlp->w2, 256, 256, 256, (int64_t)layer_byte0(1), 1};
+    jobs.j[2] = {mlp->w3, 256, 263, 288, (int64_t)layer_byte0(2), 1};
+    jobs.j[3] = {mlp->w4, 256, 256, 256, (int64_t)layer_byte0(3), 1};
+    jobs.j[4] = {mlp->wc1, 128, 280, 288, (int64_t)WPACK_FIELD_BYTES, 0};
+    jobs.j[5] = {mlp->wc2, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES, 0};
+    jobs.j[6] = {mlp->wc3, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES + C2_BYTES, 0};
     for (int i = 0; i < 7; i++) if (!jobs.j[i].w) return PNERF_ERR_ARG;
     pack_weights_kernel<<<dim3(64, 7), 256, 0, (cudaStream_t)stream>>>(jobs, (uint8_t*)wpack);
     PNERF_LAUNCH_CHECK();
@@ -616,8 +763,9 @@ extern "C" int pnerf_field_forward_tc(const pnerf_points* pts, const pnerf_camer
     const int spt = ROWS / KP;
     p.n_tiles = (S + spt - 1) / spt;
     p.slope = mode->lrelu_slope; p.softplus = mode->density_softplus; p.weight_conf = mode->weight_conf;
-    p.sigma = sigma; p.F = (__nv_bfloat16*)workspace;
-    const int grid = p.n_tiles < kSMs ? p.n_tiles : kSMs;
+    p.sigma = sigma; p.F = (__nv_bfloat16*)workspace; p.trace = g_trace;
+    const int n_super = (p.n_tiles + 1) / 2;
+    const int grid = 2 * (n_super < kSMs / 2 ? n_super : kSMs / 2);   // CTA pairs
     const size_t smem = sizeof(Smem);
     auto launch = [&](auto kern) -> int {
         PNERF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
