@@ -181,7 +181,7 @@ int pnerf_field_backward_f32(const pnerf_points* pts_h, const pnerf_camera* cam_
  * K-aggregation fused in one persistent kernel (no encoded input or activation ever reaches HBM), mlp_color +
  * rgb head in a second one.  `wpack` is the bf16 K-slab copy of the seven weight matrices made by
  * pnerf_tc_pack_weights (pnerf_tc_wpack_bytes() bytes; re-pack after every optimiser step).
- * Inference-only (saves nothing); sigma / rgb as in pnerf_field_forward_f32. */
+ * Saves nothing (inference); sigma / rgb as in pnerf_field_forward_f32.  Training: pnerf_field_forward_tc_train below. */
 int64_t pnerf_tc_wpack_bytes(void);
 int pnerf_tc_pack_weights(const pnerf_mlp* mlp_h, void* wpack, void* stream);
 int64_t pnerf_field_tc_workspace_bytes(int64_t n_samples);
@@ -189,6 +189,21 @@ int pnerf_field_forward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h,
                            const pnerf_mode* mode_h, const float* dirs, const float* sample_loc, const int* sample_pidx,
                            const int* sample_ids, int n_samples, int SR, int K, float* sigma, float* rgb, void* workspace,
                            int64_t workspace_bytes, void* stream);
+
+/* Training on the tensor-core path.  Forward = pnerf_field_forward_tc for the per-neighbour networks with every MMA operand kept
+ * in `workspace` (2.7 KB per neighbour row, tile layout of csrc/tc_layout.cuh), colour network in fp32.  Backward (what torch
+ * autograd computes for the reference through SU:190-209, SM:270-359): consumes d sigma / d rgb (by slot) and the SAME workspace,
+ * accumulates (+=) into the point gradients (may be NULL) and the MLP gradients: bf16 tcgen05 GEMMs for dgrad and wgrad of
+ * mlp_base / mlp_head, fp32 accumulation.  `workspace` must be 256-byte aligned. */
+int64_t pnerf_field_tc_train_workspace_bytes(int64_t n_samples, int K);
+int pnerf_field_forward_tc_train(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const void* wpack,
+                                 const pnerf_mode* mode_h, const float* dirs, const float* sample_loc, const int* sample_pidx,
+                                 const int* sample_ids, int n_samples, int SR, int K, float* sigma, float* rgb, void* workspace,
+                                 int64_t workspace_bytes, void* stream);
+int pnerf_field_backward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const pnerf_mode* mode_h,
+                            const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int n_samples,
+                            int SR, int K, const float* d_sigma, const float* d_rgb, float* g_embed, float* g_color, float* g_dir,
+                            float* g_conf, const pnerf_mlp_grad* g_mlp_h, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Profiling hook: when `buf` (device, pnerf_tc_trace_bytes() bytes, zero-filled) is set, CTA 0 of the next field_tc launches
  * appends clock64-stamped pipeline events per role warp (tools/tc_trace.py decodes them).  NULL switches it off. */

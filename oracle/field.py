@@ -153,11 +153,27 @@ def stclamp(x, lo=1e-4, hi=1.0):
 
 
 # ----------------------------------------------------------------------------- M1, A, M2
-def field_forward(g, W: FieldWeights, Rw2c, mode="plugin", freqs=(3, 5, 4)):
+def bf16_st(x):
+    """Round to bf16 with a straight-through gradient: where the tensor-core kernels round an MMA operand."""
+    return x + (x.to(torch.bfloat16).float() - x).detach()
+
+
+def field_forward(g, W: FieldWeights, Rw2c, mode="plugin", freqs=(3, 5, 4), bf16=False):
     """Per-neighbour network, aggregation and colour network (SM:300-366 / PA:486-662).
 
     Returns decoded (R2,SR,4) = (sigma, rgb) zero at invalid samples, valid (R2,SR) bool,
-    and extras for tests."""
+    and extras for tests.
+
+    bf16=True restates the rounding points of the tensor-core kernels (csrc/field_tc.cu): the inputs and weights
+    of mlp_base / mlp_head and the aggregated feature F_s are rounded to bf16 (fp32 accumulation, straight-through
+    gradients); the reference itself is fp32 everywhere.  It exists so that the backward kernels can be checked
+    against autograd at the SAME activations: with LeakyReLU a unit whose pre-activation rounds across zero changes
+    its gradient tenfold, which is a property of the bf16 forward, not an error of the backward."""
+    rnd = bf16_st if bf16 else (lambda t: t)
+
+    def lin_r(name, x):
+        return F.linear(rnd(x), rnd(W.p[name + ".weight"]), W.p[name + ".bias"])
+
     assert mode in ("plugin", "original")
     ff, fd, fv = freqs
     LRELU = SLOPE[mode]
@@ -176,14 +192,14 @@ def field_forward(g, W: FieldWeights, Rw2c, mode="plugin", freqs=(3, 5, 4)):
     d6 = torch.cat([d6[:, :3] @ Rn, d6[:, 3:]], dim=-1)                   # SM:312
     f = g["embed"].reshape(-1, g["embed"].shape[-1])[mflat]
     x284 = torch.cat([f, positional_encoding(f, ff), positional_encoding(d6, fd)], dim=-1)   # SM:313-317
-    h = F.leaky_relu(W.lin("mlp_base.layers.0", x284), LRELU)
-    h = F.leaky_relu(W.lin("mlp_base.layers.1", h), LRELU)               # SM:319
+    h = F.leaky_relu(lin_r("mlp_base.layers.0", x284), LRELU)
+    h = F.leaky_relu(lin_r("mlp_base.layers.1", h), LRELU)               # SM:319
     col = g["color"].reshape(-1, 3)[mflat]
     dr = g["dir"].reshape(-1, 3)[mflat] @ Rn                              # SM:330
     vk = v_ori[:, None, :].expand(-1, K, -1).reshape(-1, 3)[mflat]       # SM:331-333
     x263 = torch.cat([h, col, dr - vk, (dr * vk).sum(-1, keepdim=True)], dim=-1)            # SM:325,334
-    gfeat = F.leaky_relu(W.lin("mlp_head.layers.0", x263), LRELU)
-    gfeat = F.leaky_relu(W.lin("mlp_head.layers.1", gfeat), LRELU)       # SM:335
+    gfeat = F.leaky_relu(lin_r("mlp_head.layers.0", x263), LRELU)
+    gfeat = F.leaky_relu(lin_r("mlp_head.layers.1", gfeat), LRELU)       # SM:335
     raw = W.lin("field_output_density.net", gfeat)
     alpha = F.softplus(raw - 1) if mode == "original" else F.relu(raw)   # PA:260-265 vs SM:221
     wk = w_used.reshape(R2 * SR, K, 1)
@@ -191,7 +207,7 @@ def field_forward(g, W: FieldWeights, Rw2c, mode="plugin", freqs=(3, 5, 4)):
     sigma = (a_hold.view(R2 * SR, K, 1) * wk).sum(-2)[vflat]             # SM:344
     f_hold = torch.zeros(R2 * SR * K, gfeat.shape[-1]).index_put((mflat.nonzero()[:, 0],), gfeat)
     Fs = (f_hold.view(R2 * SR, K, -1) * wk).sum(-2)[vflat]               # SM:348-353
-    cin = torch.cat([Fs, venc[vflat]], dim=-1)                            # SM:356
+    cin = torch.cat([rnd(Fs), venc[vflat]], dim=-1)                       # SM:356
     c = F.leaky_relu(W.lin("mlp_color.layers.0", cin), LRELU)
     c = F.leaky_relu(W.lin("mlp_color.layers.1", c), LRELU)
     c = F.leaky_relu(W.lin("mlp_color.layers.2", c), LRELU)
@@ -264,11 +280,11 @@ def loss(C_full, ray_mask, gt, conf_coefficient=None, zero_eps=1e-3, zero_one_w=
 
 # ----------------------------------------------------------------------------- whole path
 def render(points, W: FieldWeights, origin, dirs, R_c2w, pidx, loc_w, ray_mask, vsize_z, SR,
-           mode="plugin", training=True, bg=None):
+           mode="plugin", training=True, bg=None, bf16=False):
     """Everything after the querier: gather -> field -> step length -> composite -> fill."""
     keep = torch.as_tensor(ray_mask).bool()
     g = gather(torch.as_tensor(pidx), points, torch.as_tensor(loc_w), dirs[keep], R_c2w, origin, SR)
-    dec, valid, ex = field_forward(g, W, points["Rw2c"], mode=mode)
+    dec, valid, ex = field_forward(g, W, points["Rw2c"], mode=mode, bf16=bf16)
     delta = ray_dist(g["loc_pers"], valid, vsize_z)
     C, bw, opacity, T_end = composite(dec, valid, delta, mode=mode, bg=bg, training=training)
     out = {"coarse_raycolor": fill_invalid(C, ray_mask, bg), "ray_mask": torch.as_tensor(ray_mask),

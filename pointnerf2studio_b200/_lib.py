@@ -85,6 +85,14 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.POINTER(MlpGrad), C.c_void_p, C.c_int64, C.c_void_p]),
+    "pnerf_field_tc_train_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int]),
+    "pnerf_field_forward_tc_train": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.c_void_p, C.POINTER(Mode),
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pnerf_field_backward_tc": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.POINTER(Mode),
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(MlpGrad), C.c_void_p, C.c_int64, C.c_void_p]),
     "pnerf_tc_set_trace": (C.c_int, [C.c_void_p]),
     "pnerf_tc_trace_bytes": (C.c_int64, []),
     "pnerf_tc_wpack_bytes": (C.c_int64, []),

@@ -175,8 +175,15 @@ __global__ void __launch_bounds__(256) conf_loss_kernel(const float* __restrict_
         const float cs = fminf(fmaxf(conf[p], 1e-4f), 1.f);              // straight-through clamp value (SM:289-292)
         const float val = fminf(fmaxf(cs, eps), 1.f - eps);              // SM:427
         part += logf(val) + logf(1.f - val);
-        if (g_conf && cs >= eps && cs <= 1.f - eps)
-            atomicAdd(g_conf + p, gscale * weight * inv_n * (1.f / val - 1.f / (1.f - val)));
+        // gradient: most slots are empty and all of those read point 0 (SU:194) -- combine equal addresses inside the warp first
+        // (one atomic per distinct point instead of thousands of serialised atomics on g_conf[0])
+        const bool live = g_conf && cs >= eps && cs <= 1.f - eps;
+        const float g = live ? gscale * weight * inv_n * (1.f / val - 1.f / (1.f - val)) : 0.f;
+        const unsigned act = __activemask();
+        const unsigned same = __match_any_sync(act, live ? p : -1);
+        float sum = 0.f;
+        for (unsigned m = same; m; m &= m - 1) sum += __shfl_sync(same, g, __ffs(m) - 1);
+        if (live && (int)(threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(g_conf + p, sum);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);

@@ -27,15 +27,15 @@
 //   TMEM      : 512 columns = 2 slots x (128 lanes x 256 fp32 columns).
 //   HBM       : in 168 B per valid row (gather) + indices; out 4 B sigma + 512 B F_s (bf16) per sample.
 #include "pnerf_common.cuh"
+#include "tc_layout.cuh"
 #include "umma.cuh"
 
 namespace pnerf {
 namespace {
 using namespace umma;
+using namespace tcl;
 
 constexpr int HID = 256;
-constexpr int ROWS = 128;
-constexpr int SLAB = ROWS * 16;                  // bytes of one 8-wide k-slab of a 128-row operand
 constexpr int KIN_PAD = 288;                     // 284 (layer 1) and 263 (layer 3) padded to 9 chunks of 32
 constexpr int A_BYTES = (KIN_PAD / 8) * SLAB;    // 73728
 // Weight stream.  A bulk copy costs ~240 clk of engine time per SM whatever its size (measured, tools/tc_microbench.py:
@@ -91,7 +91,13 @@ struct FieldParams {
     float* sigma;                   // (R*SR) by slot
     __nv_bfloat16* F;               // (S, 256) aggregated features, by compact sample index
     unsigned long long* trace;      // profiling hook (pnerf_tc_set_trace): per-warp event timelines of CTA 0, or NULL
+    // training: every MMA operand of the forward pass is kept for the backward GEMMs, in the tile layout it had in shared
+    // memory (so a backward kernel bulk-copies it straight back into an operand buffer):
+    //   save + tile * SAVE_TILE_BYTES : [X0 36 slabs | H1 32 | X3 36 | H3 32 | H4 32], slab = 128 rows x 8 bf16 (2 KB)
+    uint8_t* save;
+    float *save_w, *save_raw;       // per row (tile * 128 + row): aggregation weight, density pre-activation
 };
+
 
 // Pipeline trace: lane 0 of a role warp of CTA 0 appends (clock64 << 8 | event) to its own 2048-entry lane of the buffer.
 constexpr int TRACE_PER_WARP = 2048;
@@ -156,12 +162,22 @@ __device__ __forceinline__ void prefetch_point(const FieldParams& p, int pidx) {
     prefetch_l2(p.dir + 3 * (int64_t)pidx);
 }
 
-template <int KP>
-__device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int pidx, uint8_t* Abuf, Meta& meta, int row) {
+// A row-owning thread's view of a 128-row operand tile: slab j of the row lives at [j * SLAB + row * 16].  With SAVE the same
+// 16 bytes also go to the tile's copy in global memory (a warp stores 512 contiguous bytes per slab).
+template <bool SAVE>
+struct RowSink {
+    uint4* s; uint4* g;
+    __device__ __forceinline__ void put(int j, const uint4& v) const {
+        s[j * (SLAB / 16)] = v;
+        if (SAVE) g[j * (SLAB / 16)] = v;
+    }
+};
+
+template <int KP, bool SAVE>
+__device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int pidx, uint8_t* Abuf, uint8_t* gsave, Meta& meta, int row) {
     const int k = row % KP;
     if (k == 0) meta.slot_id[row / KP] = slot;
-    uint4* Arow = reinterpret_cast<uint4*>(Abuf + row * 16);   // slab j of this row = Arow[j * (SLAB/16)]
-    constexpr int SJ = SLAB / 16;
+    const RowSink<SAVE> A{reinterpret_cast<uint4*>(Abuf + row * 16), reinterpret_cast<uint4*>(gsave + row * 16)};
     float wraw = 0.f, cc = 1.f;
     float ex[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (pidx >= 0) {
@@ -199,14 +215,14 @@ __device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int 
         ex[6] = dr[0] * v[0] + dr[1] * v[1] + dr[2] * v[2];                                     // SM:334
         // layer-1 input [feat 32 | PE(feat, F=3) 192 | PE(dists6, F=5) 60 | 0 x 4]
 #pragma unroll
-        for (int j = 0; j < 4; j++) Arow[j * SJ] = pack8(e + 8 * j);
+        for (int j = 0; j < 4; j++) A.put(j, pack8(e + 8 * j));
 #pragma unroll
         for (int g = 0; g < 8; g++) {            // 4 embedding dims -> 24 values -> slabs 4+3g .. 4+3g+2
             float t[24];
 #pragma unroll
             for (int c = 0; c < 4; c++) pe<3>(e[4 * g + c], t + 6 * c);
 #pragma unroll
-            for (int j = 0; j < 3; j++) Arow[(4 + 3 * g + j) * SJ] = pack8(t + 8 * j);
+            for (int j = 0; j < 3; j++) A.put(4 + 3 * g + j, pack8(t + 8 * j));
         }
         {
             float t[64];
@@ -214,12 +230,12 @@ __device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int 
             for (int c = 0; c < 6; c++) pe<5>(d[c], t + 10 * c);
             t[60] = t[61] = t[62] = t[63] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; j++) Arow[(28 + j) * SJ] = pack8(t + 8 * j);
+            for (int j = 0; j < 8; j++) A.put(28 + j, pack8(t + 8 * j));
         }
     } else {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int j = 0; j < KIN_PAD / 8; j++) Arow[j * SJ] = z;
+        for (int j = 0; j < KIN_PAD / 8; j++) A.put(j, z);
     }
     float wsum = wraw;                            // SM:286: normalise over the sample's neighbours
 #pragma unroll
@@ -234,8 +250,8 @@ __device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int 
 // Hidden-layer epilogue of one 128-column half: bias + LeakyReLU in fp32, bf16 pack, next layer's A operand in place.
 // tcgen05.ld takes ~210 clk while the tensor pipe works on the other slot (60 clk idle; tools/tc_microbench.py), so the load
 // of chunk i+1 is issued before chunk i is processed (tcgen05.wait::ld waits for every outstanding load, hence the order).
-__device__ __forceinline__ void epilogue_chunk_store(float (&v)[32], const float* __restrict__ bias, float slope, uint4* Arow, int c0) {
-    constexpr int SJ = SLAB / 16;
+template <bool SAVE>
+__device__ __forceinline__ void epilogue_chunk_store(float (&v)[32], const float* __restrict__ bias, float slope, const RowSink<SAVE>& A, int c0) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
@@ -246,24 +262,25 @@ __device__ __forceinline__ void epilogue_chunk_store(float (&v)[32], const float
         x = v[j + 3] + b.w; v[j + 3] = fmaxf(x, x * slope);
     }
 #pragma unroll
-    for (int j = 0; j < 4; j++) Arow[(c0 / 8 + j) * SJ] = pack8(v + 8 * j);
+    for (int j = 0; j < 4; j++) A.put(c0 / 8 + j, pack8(v + 8 * j));
 }
+template <bool SAVE>
 __device__ __forceinline__ void epilogue_store(uint32_t tacc_lane, const float* __restrict__ bias, float slope, uint8_t* Abuf,
-                                               int row, int cbeg) {
-    uint4* Arow = reinterpret_cast<uint4*>(Abuf + row * 16);
+                                               uint8_t* gsave, int row, int cbeg) {
+    const RowSink<SAVE> Arow{reinterpret_cast<uint4*>(Abuf + row * 16), reinterpret_cast<uint4*>(gsave + row * 16)};
     float va[32], vb[32];
     tmem_ld32(tacc_lane + cbeg, va);
     tmem_ld_wait();
     tmem_ld32(tacc_lane + cbeg + 32, vb);
-    epilogue_chunk_store(va, bias, slope, Arow, cbeg);
+    epilogue_chunk_store<SAVE>(va, bias, slope, Arow, cbeg);
     tmem_ld_wait();
     tmem_ld32(tacc_lane + cbeg + 64, va);
-    epilogue_chunk_store(vb, bias, slope, Arow, cbeg + 32);
+    epilogue_chunk_store<SAVE>(vb, bias, slope, Arow, cbeg + 32);
     tmem_ld_wait();
     tmem_ld32(tacc_lane + cbeg + 96, vb);
-    epilogue_chunk_store(va, bias, slope, Arow, cbeg + 64);
+    epilogue_chunk_store<SAVE>(va, bias, slope, Arow, cbeg + 64);
     tmem_ld_wait();
-    epilogue_chunk_store(vb, bias, slope, Arow, cbeg + 96);
+    epilogue_chunk_store<SAVE>(vb, bias, slope, Arow, cbeg + 96);
 }
 
 // sum over the KP lanes of a neighbour group of 32 per-lane values; afterwards lane gl (position in its group)
@@ -287,9 +304,10 @@ __device__ __forceinline__ void butterfly(float* a, int lane) {
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
-template <int KP>
+template <int KP, bool SAVE>
 __device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)[32], const float* __restrict__ bias,
-                                                const float* __restrict__ wa, float w, float& dot, int slot, int si, int c0, int lane) {
+                                                const float* __restrict__ wa, float w, float& dot, int slot, int si, int c0, int lane,
+                                                uint4* gh4) {
     constexpr int VPL = 32 / KP;
     const int gl = lane % KP;
 #pragma unroll
@@ -297,11 +315,17 @@ __device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)
         const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
         const float4 a = *reinterpret_cast<const float4*>(wa + c0 + j);
         float x;
-        x = v[j] + b.x; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.x, dot); v[j] = x * w;
-        x = v[j + 1] + b.y; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.y, dot); v[j + 1] = x * w;
-        x = v[j + 2] + b.z; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.z, dot); v[j + 2] = x * w;
-        x = v[j + 3] + b.w; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.w, dot); v[j + 3] = x * w;
+        x = v[j] + b.x; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.x, dot); v[j] = x;
+        x = v[j + 1] + b.y; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.y, dot); v[j + 1] = x;
+        x = v[j + 2] + b.z; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.z, dot); v[j + 2] = x;
+        x = v[j + 3] + b.w; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.w, dot); v[j + 3] = x;
     }
+    if (SAVE) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) gh4[(c0 / 8 + j) * (SLAB / 16)] = pack8(v + 8 * j);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] *= w;
     butterfly<KP>(v, lane);
     if (slot >= 0) {
         __nv_bfloat16* dst = p.F + (int64_t)si * HID + c0 + gl * VPL;
@@ -316,9 +340,10 @@ __device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)
     }
 }
 
-template <int KP>
+template <int KP, bool SAVE>
 __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_t tacc_lane, const float* __restrict__ bias,
                                                    const float* __restrict__ wa, Meta& meta, int tile, int row, int half, int bar_id) {
+    uint4* gh4 = SAVE ? reinterpret_cast<uint4*>(p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)SAVE_H4 * SLAB + row * 16) : nullptr;
     constexpr int SPT = ROWS / KP;
     const int lane = threadIdx.x & 31, gl = lane % KP;
     const int sl = row / KP;
@@ -331,20 +356,21 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
     tmem_ld32(tacc_lane + cbeg, va);
     tmem_ld_wait();
     tmem_ld32(tacc_lane + cbeg + 32, vb);
-    aggregate_chunk<KP>(p, va, bias, wa, w, dot, slot, si, cbeg, lane);
+    aggregate_chunk<KP, SAVE>(p, va, bias, wa, w, dot, slot, si, cbeg, lane, gh4);
     tmem_ld_wait();
     tmem_ld32(tacc_lane + cbeg + 64, va);
-    aggregate_chunk<KP>(p, vb, bias, wa, w, dot, slot, si, cbeg + 32, lane);
+    aggregate_chunk<KP, SAVE>(p, vb, bias, wa, w, dot, slot, si, cbeg + 32, lane, gh4);
     tmem_ld_wait();
     tmem_ld32(tacc_lane + cbeg + 96, vb);
-    aggregate_chunk<KP>(p, va, bias, wa, w, dot, slot, si, cbeg + 64, lane);
+    aggregate_chunk<KP, SAVE>(p, va, bias, wa, w, dot, slot, si, cbeg + 64, lane, gh4);
     tmem_ld_wait();
-    aggregate_chunk<KP>(p, vb, bias, wa, w, dot, slot, si, cbeg + 96, lane);
+    aggregate_chunk<KP, SAVE>(p, vb, bias, wa, w, dot, slot, si, cbeg + 96, lane, gh4);
     // combine the two column halves of the density head: the upper-half warp hands its partial dot to the lower-half warp
     if (half) meta.dot_hi[row] = dot;
     asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
     if (half) return;
     const float raw = dot + meta.dot_hi[row] + __ldg(p.ba);
+    if (SAVE) { p.save_raw[(int64_t)tile * ROWS + row] = raw; p.save_w[(int64_t)tile * ROWS + row] = w; }
     const float a = p.softplus ? softplus_f(raw - 1.f) : fmaxf(raw, 0.f);   // PA:260-265 / SM:221
     float sg = w * a;
 #pragma unroll
@@ -370,7 +396,7 @@ __device__ __forceinline__ void for_each_step(int n_my, F&& fn) {
     }
 }
 
-template <int KP>
+template <int KP, bool SAVE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kernel(const FieldParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -414,7 +440,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
             prefetch_point(p, pidx1);
             if (j >= 2) { mbar_wait(&sm.a_free[s], ph[s]); ph[s] ^= 1; }
             tr.ev(1);
-            encode_tile<KP>(p, slot0, pidx0, sm.A[s], sm.meta[s][(j >> 1) & 1], tid);
+            encode_tile<KP, SAVE>(p, slot0, pidx0, sm.A[s], SAVE ? p.save + (int64_t)tile_of(j) * SAVE_TILE_BYTES : nullptr,
+                                  sm.meta[s][(j >> 1) & 1], tid);
             slot0 = slot1; pidx0 = pidx1; slot1 = slot2; pidx1 = pidx2;
             fence_proxy_async();
             __syncwarp();
@@ -437,12 +464,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
                 mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
                 tc_fence_after();
                 tr.ev(10 + L);
-                epilogue_store(tacc_lane, sm.bias[L], p.slope, sm.A[s], row, half * (HID / 2));
+                // layer L's output is the next layer's A operand: H1 (L=0), X3 = [H2 | extras] (L=1), H3 (L=2)
+                uint8_t* gsave = SAVE ? p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)(L == 0 ? SAVE_H1 : (L == 1 ? SAVE_X3 : SAVE_H3)) * SLAB
+                                      : nullptr;
+                epilogue_store<SAVE>(tacc_lane, sm.bias[L], p.slope, sm.A[s], gsave, row, half * (HID / 2));
                 if (L == 1 && half) {   // layer-3 input columns 256..287: the 7 per-row extras, then zeros
-                    uint4* Arow = reinterpret_cast<uint4*>(sm.A[s] + row * 16);
-                    Arow[32 * (SLAB / 16)] = meta.extras[row];
+                    const RowSink<SAVE> A{reinterpret_cast<uint4*>(sm.A[s] + row * 16), reinterpret_cast<uint4*>(gsave + row * 16)};
+                    A.put(32, meta.extras[row]);
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                    Arow[33 * (SLAB / 16)] = z; Arow[34 * (SLAB / 16)] = z; Arow[35 * (SLAB / 16)] = z;
+                    A.put(33, z); A.put(34, z); A.put(35, z);
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -453,7 +483,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
             mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
             tc_fence_after();
             tr.ev(13);
-            epilogue_aggregate<KP>(p, tacc_lane, sm.bias[3], sm.wa, meta, tile, row, half, 1 + s * 4 + (warp & 3));
+            epilogue_aggregate<KP, SAVE>(p, tacc_lane, sm.bias[3], sm.wa, meta, tile, row, half, 1 + s * 4 + (warp & 3));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&sm.acc_empty[s], 0);
@@ -743,15 +773,12 @@ extern "C" int pnerf_tc_pack_weights(const pnerf_mlp* mlp, void* wpack, void* st
 
 extern "C" int64_t pnerf_field_tc_workspace_bytes(int64_t n_samples) { return align_up(n_samples * HID * 2, 256) + 256; }
 
-extern "C" int pnerf_field_forward_tc(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack,
-                                      const pnerf_mode* mode, const float* dirs, const float* sample_loc, const int* sample_pidx,
-                                      const int* sample_ids, int S, int SR, int K, float* sigma, float* rgb, void* workspace,
-                                      int64_t workspace_bytes, void* stream) {
-    if (!pts || !cam || !mlp || !wpack || !mode || S < 0 || K <= 0 || K > 32 || SR <= 0) return PNERF_ERR_ARG;
-    if (S == 0) return PNERF_OK;
-    if (!workspace || workspace_bytes < pnerf_field_tc_workspace_bytes(S)) return PNERF_ERR_WORKSPACE;
-    if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;   // lrelu(x) = max(x, slope x)
-    cudaStream_t st = (cudaStream_t)stream;
+namespace pnerf {
+// Fused per-neighbour networks (sigma by slot + F (S,256) bf16); with `save` != NULL every MMA operand is kept for the backward
+// pass (training); with `color` the tensor-core colour network follows (inference).
+int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack, const pnerf_mode* mode,
+                    const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S, int SR, int K,
+                    float* sigma, float* rgb, void* F, uint8_t* save, float* save_w, float* save_raw, bool color, cudaStream_t st) {
     const int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
     FieldParams p;
     p.xyz = pts->xyz; p.embed = pts->embed; p.color = pts->color; p.dir = pts->dir; p.conf = pts->conf;
@@ -763,7 +790,8 @@ extern "C" int pnerf_field_forward_tc(const pnerf_points* pts, const pnerf_camer
     const int spt = ROWS / KP;
     p.n_tiles = (S + spt - 1) / spt;
     p.slope = mode->lrelu_slope; p.softplus = mode->density_softplus; p.weight_conf = mode->weight_conf;
-    p.sigma = sigma; p.F = (__nv_bfloat16*)workspace; p.trace = g_trace;
+    p.sigma = sigma; p.F = (__nv_bfloat16*)F; p.trace = g_trace;
+    p.save = save; p.save_w = save_w; p.save_raw = save_raw;
     const int n_super = (p.n_tiles + 1) / 2;
     const int grid = 2 * (n_super < kSMs / 2 ? n_super : kSMs / 2);   // CTA pairs
     const size_t smem = sizeof(Smem);
@@ -773,8 +801,10 @@ extern "C" int pnerf_field_forward_tc(const pnerf_points* pts, const pnerf_camer
         PNERF_LAUNCH_CHECK();
         return PNERF_OK;
     };
-    int rc = KP == 8 ? launch(field_tc_kernel<8>) : (KP == 16 ? launch(field_tc_kernel<16>) : launch(field_tc_kernel<32>));
-    if (rc) return rc;
+    int rc;
+    if (save) rc = KP == 8 ? launch(field_tc_kernel<8, true>) : (KP == 16 ? launch(field_tc_kernel<16, true>) : launch(field_tc_kernel<32, true>));
+    else rc = KP == 8 ? launch(field_tc_kernel<8, false>) : (KP == 16 ? launch(field_tc_kernel<16, false>) : launch(field_tc_kernel<32, false>));
+    if (rc || !color) return rc;
 
     ColorParams c;
     c.F = p.F; c.sample_ids = sample_ids; c.dirs = dirs;
@@ -788,4 +818,17 @@ extern "C" int pnerf_field_forward_tc(const pnerf_points* pts, const pnerf_camer
     color_tc_kernel<<<cgrid, 128, csmem, st>>>(c);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
+}
+}  // namespace pnerf
+
+extern "C" int pnerf_field_forward_tc(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack,
+                                      const pnerf_mode* mode, const float* dirs, const float* sample_loc, const int* sample_pidx,
+                                      const int* sample_ids, int S, int SR, int K, float* sigma, float* rgb, void* workspace,
+                                      int64_t workspace_bytes, void* stream) {
+    if (!pts || !cam || !mlp || !wpack || !mode || S < 0 || K <= 0 || K > 32 || SR <= 0) return PNERF_ERR_ARG;
+    if (S == 0) return PNERF_OK;
+    if (!workspace || workspace_bytes < pnerf_field_tc_workspace_bytes(S)) return PNERF_ERR_WORKSPACE;
+    if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;   // lrelu(x) = max(x, slope x)
+    return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, SR, K, sigma, rgb, workspace, nullptr,
+                           nullptr, nullptr, true, (cudaStream_t)stream);
 }

@@ -1,0 +1,558 @@
+// Tensor-core training path of the per-neighbour networks (row BWD of SURVEY.md 8a): what torch autograd does for the
+// reference through SU:190-209 and SM:270-353 -- dgrad and wgrad of mlp_base / mlp_head, the density head, the K-aggregation
+// and the scatter-add of the row gradients into the neural-point tensors -- as bf16 tcgen05 GEMMs over the operand tiles the
+// forward kernel kept (field_tc.cu, SAVE mode), fp32 accumulation in TMEM.
+//
+//   agg_bwd_kernel   (SIMT)  delta4 = (w dF_s + w d sigma a' wa) * lrelu'(h4)  per row; d wa, d ba; d w (confidence, original flow)
+//   tile_gemm_kernel (TC)    delta_{L-1} = lrelu'(h_{L-1}) * (delta_L W_L)   per 128-row tile: the layer's transposed weights stay
+//                            resident in shared memory (128 KB), a tile arrives as ONE 64 KB bulk copy, two TMEM accumulators
+//                            so a tile's epilogue overlaps the next tile's copy + MMAs
+//   wgrad_tc_kernel  (TC)    dW_L = delta_L^T X_{L-1}: both operands are the saved tiles read as MN-major operands (the k-slab
+//                            layout IS the canonical no-swizzle MN-major layout with LBO and SBO swapped), K = the 128 rows of a
+//                            tile, accumulated over a CTA's tiles in TMEM (128 x 288 fp32), fp32 red.add into dW at the end
+//   colsum_kernel    (SIMT)  d b_L = column sums of delta_L
+//   scatter_kernel   (SIMT)  d embed (raw + through the positional encoding), d color, d dir, d conf -> atomics by point id
+// The colour network runs in fp32 SIMT (field_f32.cu): 1/26 of the per-neighbour FLOPs.
+#include "pnerf_common.cuh"
+#include "tc_layout.cuh"
+#include "umma.cuh"
+
+namespace pnerf {
+namespace {
+using namespace umma;
+using namespace tcl;
+
+constexpr int HID = 256;
+constexpr int NX0 = 224;                       // columns of the layer-1 input that carry a gradient: feat 32 + PE(feat) 192
+constexpr int64_t WB4 = 0, WB3 = 131072, WB2 = 262144, WB1 = 393216, WBWD_BYTES = 393216 + 32 * NX0 * 16;
+
+struct Cam { float o[3]; float Rc[9]; float Rw[9]; };
+Cam make_cam(const pnerf_points* pts, const pnerf_camera* cam) {
+    Cam c;
+    for (int i = 0; i < 3; i++) c.o[i] = cam->origin[i];
+    for (int i = 0; i < 9; i++) { c.Rc[i] = cam->R_c2w[i]; c.Rw[i] = pts->Rw2c[i]; }
+    return c;
+}
+__device__ __forceinline__ void rot_w2c(const Cam& c, const float* u, float* out) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) out[j] = u[0] * c.Rw[3 * j] + u[1] * c.Rw[3 * j + 1] + u[2] * c.Rw[3 * j + 2];
+}
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    uint4 r;
+    r.x = pack_bf16(v[0], v[1]); r.y = pack_bf16(v[2], v[3]); r.z = pack_bf16(v[4], v[5]); r.w = pack_bf16(v[6], v[7]);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------- transposed weight pack
+// Bt[k/8][n][8] with Bt(n, k) = W[k][n]: k = output feature of the forward layer (256), n = input feature (first `n_cols`).
+struct PackT { const float* w; int in_dim, n_cols; int64_t off; };
+struct PackTs { PackT j[4]; };
+__global__ void __launch_bounds__(256) pack_bwd_kernel(PackTs jobs, uint8_t* __restrict__ dst) {
+    const PackT jb = jobs.j[blockIdx.y];
+    const int total = HID * jb.n_cols;
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst + jb.off);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i % jb.n_cols, k = i / jb.n_cols;
+        d[((int64_t)(k >> 3) * jb.n_cols + n) * 8 + (k & 7)] = __float2bfloat16(jb.w[(int64_t)k * jb.in_dim + n]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- aggregation backward
+struct AggBwd {
+    const uint8_t* save; const float *save_w, *save_raw;
+    const int* sample_ids; const float* d_sigma; const float* dF; int ldF;
+    const float* wa;
+    int S, KP, n_tiles, softplus; float slope;
+    uint8_t* d4; float *dwa, *dba, *dw_rows;
+};
+__global__ void __launch_bounds__(128) agg_bwd_kernel(const AggBwd p) {
+    __shared__ float s_wa[HID];
+    __shared__ float s_draw[ROWS];
+    const int row = threadIdx.x;
+    s_wa[row] = p.wa[row]; s_wa[row + 128] = p.wa[row + 128];
+    float acc_wa[2] = {0.f, 0.f}, acc_ba = 0.f;
+    const int spt = ROWS / p.KP;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        const int64_t grow = (int64_t)tile * ROWS + row;
+        const int si = tile * spt + row / p.KP;
+        const float w = p.save_w[grow], raw = p.save_raw[grow];
+        const bool live = si < p.S;
+        const float ds = live ? p.d_sigma[p.sample_ids[si]] : 0.f;
+        const float a = p.softplus ? softplus_f(raw - 1.f) : fmaxf(raw, 0.f);
+        const float dact = p.softplus ? sigmoid_f(raw - 1.f) : (raw > 0.f ? 1.f : 0.f);
+        const float draw = ds * w * dact;
+        const float4* dFrow = reinterpret_cast<const float4*>(p.dF + (int64_t)(live ? si : 0) * p.ldF);
+        const uint4* h4 = reinterpret_cast<const uint4*>(p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)SAVE_H4 * SLAB + row * 16);
+        uint4* out = reinterpret_cast<uint4*>(p.d4 + (int64_t)tile * DELTA_TILE_BYTES + row * 16);
+        float dwk = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < HID / 8; j++) {
+            float h[8], g[8];
+            unpack8(h4[j * (SLAB / 16)], h);
+            float4 d0 = make_float4(0.f, 0.f, 0.f, 0.f), d1 = d0;
+            if (live) { d0 = __ldg(dFrow + 2 * j); d1 = __ldg(dFrow + 2 * j + 1); }
+            const float df[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                dwk = fmaf(df[i], h[i], dwk);
+                g[i] = fmaf(w, df[i], draw * s_wa[8 * j + i]) * (h[i] > 0.f ? 1.f : p.slope);
+            }
+            out[j * (SLAB / 16)] = pack8(g);
+        }
+        p.dw_rows[grow] = dwk + ds * a;
+        s_draw[row] = draw;
+        __syncthreads();
+        // d wa[c] += sum_rows draw_r h4[r][c]: thread t owns columns 2t, 2t+1
+        const __nv_bfloat16* ht = reinterpret_cast<const __nv_bfloat16*>(p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)SAVE_H4 * SLAB);
+        const int c = 2 * row;
+        const __nv_bfloat16* col = ht + (c >> 3) * (SLAB / 2) + (c & 7);
+        float s0 = 0.f, s1 = 0.f, sb = 0.f;
+        for (int r = 0; r < ROWS; r++) {
+            const float d = s_draw[r];
+            const __nv_bfloat162 hv = *reinterpret_cast<const __nv_bfloat162*>(col + r * 8);
+            s0 = fmaf(d, __low2float(hv), s0);
+            s1 = fmaf(d, __high2float(hv), s1);
+            sb += d;
+        }
+        acc_wa[0] += s0; acc_wa[1] += s1; acc_ba += sb;
+    }
+    if (p.dwa) {
+        atomicAdd(p.dwa + 2 * row, acc_wa[0]); atomicAdd(p.dwa + 2 * row + 1, acc_wa[1]);
+        if (row == 0) atomicAdd(p.dba, acc_ba);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- dgrad tile GEMM
+struct GemmP {
+    const uint8_t* in; int64_t in_stride;            // 128 x 256 bf16 operand tiles (K-major k-slabs), 64 KB each
+    const uint8_t* mask; int64_t mask_stride;        // tiles whose sign gives lrelu' (same layout), or NULL
+    uint8_t* out_bf; int64_t out_stride;             // bf16 tile output, or
+    float* out_f32; int ld_f32;                      // fp32 row-major output (row = tile * 128 + r)
+    const uint8_t* w; int N; int n_tiles; float slope;
+};
+struct GemmSmem {
+    uint8_t W[32 * HID * 16];
+    uint8_t A[DELTA_TILE_BYTES];
+    uint64_t w_bar, a_full, a_free, acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(256, 1) tile_gemm_kernel(const GemmP p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_my = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (tid == 0) {
+        mbar_init(&sm.w_bar, 1); mbar_init(&sm.a_full, 1); mbar_init(&sm.a_free, 1);
+        for (int b = 0; b < 2; b++) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    const int N = p.N;
+    if (warp == 0) {
+        if (lane == 0 && n_my > 0) {
+            const uint32_t wbytes = (uint32_t)(32 * N * 16);
+            mbar_arrive_expect_tx(&sm.w_bar, wbytes);
+            for (int q = 0; q < 4; q++) bulk_g2s(sm.W + q * (wbytes / 4), p.w + q * (wbytes / 4), wbytes / 4, &sm.w_bar);
+            mbar_wait(&sm.w_bar, 0);
+            const uint32_t idesc = make_idesc_bf16(ROWS, N);
+            const uint32_t a_base = smem_u32(sm.A), w_base = smem_u32(sm.W);
+            for (int i = 0; i < n_my; i++) {
+                const int tile = (int)blockIdx.x + i * (int)gridDim.x, b = i & 1;
+                if (i > 0) mbar_wait(&sm.a_free, (uint32_t)((i - 1) & 1));
+                mbar_arrive_expect_tx(&sm.a_full, (uint32_t)DELTA_TILE_BYTES);
+                bulk_g2s(sm.A, p.in + (int64_t)tile * p.in_stride, (uint32_t)DELTA_TILE_BYTES, &sm.a_full);
+                mbar_wait(&sm.a_full, (uint32_t)(i & 1));
+                if (i >= 2) mbar_wait(&sm.acc_empty[b], (uint32_t)(((i >> 1) - 1) & 1));
+                tc_fence_after();
+                for (int ks = 0; ks < HID / 16; ks++) {
+                    const uint64_t ad = make_smem_desc(a_base + (uint32_t)(ks * 2 * SLAB), SLAB, 128);
+                    const uint64_t bd = make_smem_desc(w_base + (uint32_t)(ks * 2 * N * 16), (uint32_t)(N * 16), 128);
+                    mma_bf16(tmem + (uint32_t)(b * HID), ad, bd, idesc, (uint32_t)(ks > 0));
+                }
+                mma_commit(&sm.a_free);
+                mma_commit(&sm.acc_full[b]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int row = (warp & 3) * 32 + lane;
+        for (int i = 0; i < n_my; i++) {
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x, b = i & 1;
+            mbar_wait(&sm.acc_full[b], (uint32_t)((i >> 1) & 1));
+            tc_fence_after();
+            const uint32_t tacc = tmem + (uint32_t)(b * HID) + ((uint32_t)((warp & 3) * 32) << 16);
+            const uint4* mrow = p.mask ? reinterpret_cast<const uint4*>(p.mask + (int64_t)tile * p.mask_stride + row * 16) : nullptr;
+            uint4* orow = p.out_bf ? reinterpret_cast<uint4*>(p.out_bf + (int64_t)tile * p.out_stride + row * 16) : nullptr;
+            float* frow = p.out_f32 ? p.out_f32 + ((int64_t)tile * ROWS + row) * p.ld_f32 : nullptr;
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                float v[32];
+                tmem_ld32(tacc + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (mrow) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float h[8];
+                        unpack8(__ldg(mrow + (c0 / 8 + j) * (SLAB / 16)), h);
+#pragma unroll
+                        for (int e = 0; e < 8; e++) v[8 * j + e] *= (h[e] > 0.f ? 1.f : p.slope);
+                    }
+                }
+                if (orow) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) orow[(c0 / 8 + j) * (SLAB / 16)] = pack8(v + 8 * j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) *reinterpret_cast<float4*>(frow + c0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_empty[b]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- wgrad
+struct WgradP {
+    const uint8_t* d[4];            // delta_1 .. delta_4 tiles
+    const uint8_t* save;
+    float* dW[4];                   // (256, in_dim) fp32, accumulated into
+    int in_dim[4], xoff[4], xslabs[4];
+    int n_tiles;
+};
+struct WgSmem {
+    uint8_t D[2][16 * SLAB];        // one 128-column half of a delta tile: M = 128 output features, K = 128 rows
+    uint8_t X[2][36 * SLAB];        // the layer's input tile: N = up to 288 input features, K = 128 rows
+    uint64_t full[2], empty[2], done;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int job = (int)blockIdx.x & 7, L = job >> 1, h = job & 1;
+    const int part = (int)blockIdx.x >> 3, parts = (int)gridDim.x >> 3;
+    const int n_my = p.n_tiles > part ? (p.n_tiles - part + parts - 1) / parts : 0;
+    const int xslabs = p.xslabs[L];
+    if (tid == 0) {
+        for (int s = 0; s < 2; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        mbar_init(&sm.done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    if (warp == 0) {
+        if (lane == 0) {            // producer
+            for (int i = 0; i < n_my; i++) {
+                const int tile = part + i * parts, s = i & 1;
+                if (i >= 2) mbar_wait(&sm.empty[s], (uint32_t)(((i >> 1) - 1) & 1));
+                const uint32_t xbytes = (uint32_t)(xslabs * SLAB);
+                mbar_arrive_expect_tx(&sm.full[s], 16u * SLAB + xbytes);
+                bulk_g2s(sm.D[s], p.d[L] + (int64_t)tile * DELTA_TILE_BYTES + (int64_t)h * 16 * SLAB, 16u * SLAB, &sm.full[s]);
+                bulk_g2s(sm.X[s], p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)p.xoff[L] * SLAB, xbytes, &sm.full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && n_my > 0) {   // MMA issuer: both operands MN-major (k = tile rows): LBO = 128 (next 8 rows), SBO = SLAB (next 8 features)
+            const uint32_t mn = (1u << 15) | (1u << 16);
+            const uint32_t idesc_main = make_idesc_bf16(ROWS, 256) | mn, idesc_tail = make_idesc_bf16(ROWS, 32) | mn;
+            for (int i = 0; i < n_my; i++) {
+                const int s = i & 1;
+                mbar_wait(&sm.full[s], (uint32_t)((i >> 1) & 1));
+                tc_fence_after();
+                const uint32_t d_base = smem_u32(sm.D[s]), x_base = smem_u32(sm.X[s]);
+                for (int ks = 0; ks < ROWS / 16; ks++) {
+                    const uint64_t ad = make_smem_desc(d_base + (uint32_t)(ks * 256), 128, SLAB);
+                    const uint64_t bd = make_smem_desc(x_base + (uint32_t)(ks * 256), 128, SLAB);
+                    mma_bf16(tmem, ad, bd, idesc_main, (uint32_t)((i | ks) > 0));
+                    if (xslabs > 32) {
+                        const uint64_t bt = make_smem_desc(x_base + (uint32_t)(32 * SLAB + ks * 256), 128, SLAB);
+                        mma_bf16(tmem + 256u, ad, bt, idesc_tail, (uint32_t)((i | ks) > 0));
+                    }
+                }
+                mma_commit(&sm.empty[s]);
+            }
+            mma_commit(&sm.done);
+        }
+    } else if (warp >= 4 && n_my > 0) {
+        mbar_wait(&sm.done, 0);
+        tc_fence_after();
+        const int o = h * 128 + (warp & 3) * 32 + lane;          // output feature = accumulator lane
+        const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        float* dst = p.dW[L] + (int64_t)o * p.in_dim[L];
+        const int in_dim = p.in_dim[L];
+#pragma unroll 1
+        for (int c0 = 0; c0 < xslabs * 8; c0 += 32) {
+            float v[32];
+            tmem_ld32(tacc + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (c0 + j < in_dim) atomicAdd(dst + c0 + j, v[j]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- bias gradients
+// db_L[c] = sum over rows of delta_L[r][c].  Thread = (slab, 16-row group); block = one tile at a time.
+struct ColsumP { const uint8_t* d[4]; float* db[4]; int n_tiles; };
+__global__ void __launch_bounds__(256) colsum_kernel(const ColsumP p) {
+    __shared__ float s_part[8][HID];
+    const int L = blockIdx.y, t = threadIdx.x;
+    const int slab = t >> 3, rg = t & 7;
+    float acc[8] = {};
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.d[L] + (int64_t)tile * DELTA_TILE_BYTES + (int64_t)slab * SLAB) + rg * 16;
+#pragma unroll 4
+        for (int r = 0; r < 16; r++) {
+            float f[8];
+            unpack8(__ldg(src + r), f);
+#pragma unroll
+            for (int e = 0; e < 8; e++) acc[e] += f[e];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++) s_part[rg][slab * 8 + e] = acc[e];
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; g++) s += s_part[g][t];
+    if (p.db[L]) atomicAdd(p.db[L] + t, s);
+}
+
+// ---------------------------------------------------------------------------------------------- scatter to the points
+struct ScatterP {
+    Cam cam;
+    const int *sample_pidx, *sample_ids; const float* dirs;
+    const float *embed, *conf;
+    const float* dx0;               // (rows, 224) fp32: gradient of [feat 32 | PE(feat) 192]
+    const uint8_t* d3;              // delta_3 tiles: gradient of mlp_head layer-0 pre-activations
+    const float* w3;                // mlp_head.layers.0 weight (256, 263): columns 256..262 multiply the 7 extras
+    const float *dw_rows, *save_w;
+    int S, SR, K, KP, n_tiles, weight_conf;
+    float *g_embed, *g_color, *g_dir, *g_conf;
+};
+__global__ void __launch_bounds__(128) scatter_kernel(const ScatterP p) {
+    __shared__ float s_w3e[HID][8];
+    for (int i = threadIdx.x; i < HID * 8; i += 128) { const int c = i >> 3, j = i & 7; s_w3e[c][j] = j < 7 ? p.w3[(int64_t)c * 263 + 256 + j] : 0.f; }
+    __syncthreads();
+    const int row = threadIdx.x;
+    const int spt = ROWS / p.KP;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int si = tile * spt + row / p.KP, k = row % p.KP;
+        if (si >= p.S || k >= p.K) continue;
+        const int slot = p.sample_ids[si];
+        const int pt = p.sample_pidx[(int64_t)slot * p.K + k];
+        if (pt < 0) continue;
+        const int64_t grow = (int64_t)tile * ROWS + row;
+        if (p.g_embed) {
+            const float* dx = p.dx0 + grow * NX0;
+            const float4* e4 = reinterpret_cast<const float4*>(p.embed + (int64_t)pt * 32);
+            float4* g4 = reinterpret_cast<float4*>(p.g_embed + (int64_t)pt * 32);
+#pragma unroll 2
+            for (int q = 0; q < 8; q++) {
+                const float4 ev = __ldg(e4 + q);
+                const float e[4] = {ev.x, ev.y, ev.z, ev.w};
+                float g[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int d = 4 * q + i;
+                    float acc = dx[d];
+                    float sn, cs;
+                    __sincosf(e[i], &sn, &cs);             // as the forward encoder: one sincos + double-angle recurrences
+#pragma unroll
+                    for (int f = 0; f < 3; f++) {          // d sin(2^f x) = 2^f cos, d cos(2^f x) = -2^f sin (SU:61-67 layout)
+                        const float sc = (float)(1 << f);
+                        acc = fmaf(dx[32 + (d * 3 + f) * 2], sc * cs, acc);
+                        acc = fmaf(dx[32 + (d * 3 + f) * 2 + 1], -sc * sn, acc);
+                        const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
+                        sn = s2; cs = c2;
+                    }
+                    g[i] = acc;
+                }
+                atomicAdd(g4 + q, make_float4(g[0], g[1], g[2], g[3]));
+            }
+        }
+        if (p.g_color || p.g_dir) {
+            float de[7] = {};
+            const uint4* drow = reinterpret_cast<const uint4*>(p.d3 + (int64_t)tile * DELTA_TILE_BYTES + row * 16);
+#pragma unroll 2
+            for (int j = 0; j < HID / 8; j++) {
+                float f[8];
+                unpack8(__ldg(drow + j * (SLAB / 16)), f);
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+#pragma unroll
+                    for (int x = 0; x < 7; x++) de[x] = fmaf(f[e], s_w3e[8 * j + e][x], de[x]);
+            }
+            if (p.g_color) { atomicAdd(p.g_color + 3 * (int64_t)pt, de[0]); atomicAdd(p.g_color + 3 * (int64_t)pt + 1, de[1]); atomicAdd(p.g_color + 3 * (int64_t)pt + 2, de[2]); }
+            if (p.g_dir) {
+                // dr = dir . Rn ; e[3+j] = dr_j - v_j ; e[6] = <dr, v>  ->  d dr_j = de[3+j] + de[6] v_j ; d dir_i = sum_j d dr_j Rw2c[j][i]
+                const int ray = slot / p.SR;
+                const float rd[3] = {p.dirs[3 * ray], p.dirs[3 * ray + 1], p.dirs[3 * ray + 2]};
+                float v[3];
+                rot_w2c(p.cam, rd, v);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    float gi = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) gi = fmaf(de[3 + j] + de[6] * v[j], p.cam.Rw[3 * j + i], gi);
+                    atomicAdd(p.g_dir + 3 * (int64_t)pt + i, gi);
+                }
+            }
+        }
+        if (p.g_conf && p.weight_conf) {   // w = wn * clamp(conf): d conf = d w * wn (straight-through clamp, PA:740-742)
+            const float cc = fminf(fmaxf(p.conf[pt], 1e-4f), 1.f);
+            atomicAdd(p.g_conf + pt, p.dw_rows[grow] * (p.save_w[grow] / cc));
+        }
+    }
+}
+
+struct TrainWs {
+    uint8_t* F; uint8_t* save; float *save_w, *save_raw; float* color; uint8_t* d[4]; float* dx0; float* dw_rows; uint8_t* wbwd;
+    int64_t total;
+};
+TrainWs carve_train(void* base, int64_t S, int K) {
+    const int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+    // the forward kernel works on CTA pairs: with an odd tile count the peer CTA still encodes (and saves) one all-masked tile
+    const int64_t spt = ROWS / KP, n_tiles = ((S + spt - 1) / spt + 1) / 2 * 2, rows = n_tiles * ROWS;
+    uint8_t* p = (uint8_t*)base;
+    TrainWs w;
+    auto take = [&](int64_t bytes) { uint8_t* r = p; p += align_up(bytes, 1024); return r; };
+    w.F = take(S * HID * 2);
+    w.save = take(n_tiles * SAVE_TILE_BYTES);
+    w.save_w = (float*)take(rows * 4);
+    w.save_raw = (float*)take(rows * 4);
+    w.color = (float*)take(color_f32_ws_floats(S) * 4);
+    for (int i = 0; i < 4; i++) w.d[i] = take(n_tiles * DELTA_TILE_BYTES);
+    w.dx0 = (float*)take(rows * NX0 * 4);
+    w.dw_rows = (float*)take(rows * 4);
+    w.wbwd = take(WBWD_BYTES);
+    w.total = p - (uint8_t*)base;
+    return w;
+}
+}  // namespace
+}  // namespace pnerf
+
+using namespace pnerf;
+
+extern "C" int64_t pnerf_field_tc_train_workspace_bytes(int64_t n_samples, int K) { return carve_train(nullptr, n_samples, K).total + 1024; }
+
+extern "C" int pnerf_field_forward_tc_train(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack,
+                                            const pnerf_mode* mode, const float* dirs, const float* sample_loc, const int* sample_pidx,
+                                            const int* sample_ids, int S, int SR, int K, float* sigma, float* rgb, void* workspace,
+                                            int64_t workspace_bytes, void* stream) {
+    if (!pts || !cam || !mlp || !wpack || !mode || S < 0 || K <= 0 || K > 32 || SR <= 0) return PNERF_ERR_ARG;
+    if (S == 0) return PNERF_OK;
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < pnerf_field_tc_train_workspace_bytes(S, K)) return PNERF_ERR_WORKSPACE;
+    if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    TrainWs w = carve_train(workspace, S, K);
+    int rc = field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, SR, K, sigma, rgb, w.F, w.save, w.save_w,
+                             w.save_raw, false, st);
+    if (rc) return rc;
+    return color_forward_f32(pts, cam, mlp, mode, dirs, sample_ids, S, SR, w.F, w.color, rgb, st);
+}
+
+extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const pnerf_mode* mode,
+                                       const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S,
+                                       int SR, int K, const float* d_sigma, const float* d_rgb, float* g_embed, float* g_color,
+                                       float* g_dir, float* g_conf, const pnerf_mlp_grad* gm, void* workspace, int64_t workspace_bytes,
+                                       void* stream) {
+    if (!pts || !cam || !mlp || !mode || !gm || S < 0 || K <= 0 || K > 32 || SR <= 0 || !d_sigma || !d_rgb) return PNERF_ERR_ARG;
+    if (S == 0) return PNERF_OK;
+    if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < pnerf_field_tc_train_workspace_bytes(S, K)) return PNERF_ERR_WORKSPACE;
+    (void)sample_loc;
+    cudaStream_t st = (cudaStream_t)stream;
+    TrainWs w = carve_train(workspace, S, K);
+    const int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+    const int n_tiles = (int)((S + ROWS / KP - 1) / (ROWS / KP));
+    // colour network (fp32) -> dF_s
+    const float* dF; int ldF;
+    int rc = color_backward_f32(mlp, gm, mode, sample_ids, S, d_rgb, w.color, &dF, &ldF, st);
+    if (rc) return rc;
+    // transposed bf16 weights of the four 256-wide layers
+    PackTs jobs;
+    jobs.j[0] = {mlp->w4, 256, 256, WB4}; jobs.j[1] = {mlp->w3, 263, 256, WB3}; jobs.j[2] = {mlp->w2, 256, 256, WB2}; jobs.j[3] = {mlp->w1, 284, NX0, WB1};
+    pack_bwd_kernel<<<dim3(64, 4), 256, 0, st>>>(jobs, w.wbwd);
+    PNERF_LAUNCH_CHECK();
+    // aggregation + density head backward -> delta_4
+    AggBwd a;
+    a.save = w.save; a.save_w = w.save_w; a.save_raw = w.save_raw; a.sample_ids = sample_ids; a.d_sigma = d_sigma; a.dF = dF; a.ldF = ldF;
+    a.wa = mlp->wa; a.S = S; a.KP = KP; a.n_tiles = n_tiles; a.softplus = mode->density_softplus; a.slope = mode->lrelu_slope;
+    a.d4 = w.d[3]; a.dwa = gm->wa; a.dba = gm->ba; a.dw_rows = w.dw_rows;
+    agg_bwd_kernel<<<n_tiles < kSMs * 8 ? n_tiles : kSMs * 8, 128, 0, st>>>(a);
+    PNERF_LAUNCH_CHECK();
+    // dgrad chain
+    const size_t gsm = sizeof(GemmSmem);
+    PNERF_CUDA(cudaFuncSetAttribute(tile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    const int ggrid = n_tiles < kSMs ? n_tiles : kSMs;
+    auto dgrad = [&](const uint8_t* in, int mask_slab, uint8_t* out_bf, float* out_f32, int64_t wb, int N) -> int {
+        GemmP g;
+        g.in = in; g.in_stride = DELTA_TILE_BYTES;
+        g.mask = mask_slab >= 0 ? w.save + (int64_t)mask_slab * SLAB : nullptr; g.mask_stride = SAVE_TILE_BYTES;
+        g.out_bf = out_bf; g.out_stride = DELTA_TILE_BYTES; g.out_f32 = out_f32; g.ld_f32 = NX0;
+        g.w = w.wbwd + wb; g.N = N; g.n_tiles = n_tiles; g.slope = mode->lrelu_slope;
+        tile_gemm_kernel<<<ggrid, 256, gsm, st>>>(g);
+        PNERF_LAUNCH_CHECK();
+        return PNERF_OK;
+    };
+    if ((rc = dgrad(w.d[3], SAVE_H3, w.d[2], nullptr, WB4, 256))) return rc;      // delta_3 = lrelu'(h3) * (delta_4 W4)
+    if ((rc = dgrad(w.d[2], SAVE_X3, w.d[1], nullptr, WB3, 256))) return rc;      // delta_2 = lrelu'(h2) * (delta_3 W3[:, :256])
+    if ((rc = dgrad(w.d[1], SAVE_H1, w.d[0], nullptr, WB2, 256))) return rc;      // delta_1 = lrelu'(h1) * (delta_2 W2)
+    if (g_embed && (rc = dgrad(w.d[0], -1, nullptr, w.dx0, WB1, NX0))) return rc; // d x0[:, :224] = delta_1 W1[:, :224]
+    // wgrad + bias gradients
+    if (gm->w1 && gm->w2 && gm->w3 && gm->w4) {
+        WgradP g;
+        for (int i = 0; i < 4; i++) g.d[i] = w.d[i];
+        g.save = w.save; g.n_tiles = n_tiles;
+        g.dW[0] = gm->w1; g.dW[1] = gm->w2; g.dW[2] = gm->w3; g.dW[3] = gm->w4;
+        g.in_dim[0] = 284; g.in_dim[1] = 256; g.in_dim[2] = 263; g.in_dim[3] = 256;
+        g.xoff[0] = SAVE_X0; g.xoff[1] = SAVE_H1; g.xoff[2] = SAVE_X3; g.xoff[3] = SAVE_H3;
+        g.xslabs[0] = 36; g.xslabs[1] = 32; g.xslabs[2] = 36; g.xslabs[3] = 32;
+        const size_t wsm = sizeof(WgSmem);
+        PNERF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+        wgrad_tc_kernel<<<8 * (kSMs / 8), 256, wsm, st>>>(g);
+        PNERF_LAUNCH_CHECK();
+        ColsumP c;
+        for (int i = 0; i < 4; i++) c.d[i] = w.d[i];
+        c.db[0] = gm->b1; c.db[1] = gm->b2; c.db[2] = gm->b3; c.db[3] = gm->b4; c.n_tiles = n_tiles;
+        colsum_kernel<<<dim3(n_tiles < 64 ? n_tiles : 64, 4), 256, 0, st>>>(c);
+        PNERF_LAUNCH_CHECK();
+    }
+    // point gradients
+    if (g_embed || g_color || g_dir || (g_conf && mode->weight_conf)) {
+        ScatterP s;
+        s.cam = make_cam(pts, cam);
+        s.sample_pidx = sample_pidx; s.sample_ids = sample_ids; s.dirs = dirs; s.embed = pts->embed; s.conf = pts->conf;
+        s.dx0 = w.dx0; s.d3 = w.d[2]; s.w3 = mlp->w3; s.dw_rows = w.dw_rows; s.save_w = w.save_w;
+        s.S = S; s.SR = SR; s.K = K; s.KP = KP; s.n_tiles = n_tiles; s.weight_conf = mode->weight_conf;
+        s.g_embed = g_embed; s.g_color = g_color; s.g_dir = g_dir; s.g_conf = g_conf;
+        scatter_kernel<<<n_tiles < kSMs * 8 ? n_tiles : kSMs * 8, 128, 0, st>>>(s);
+        PNERF_LAUNCH_CHECK();
+    }
+    return PNERF_OK;
+}

@@ -203,11 +203,18 @@ class NeuralPoints(nn.Module):
         return ranges_tensor, vsize_np, f.dim
 
     @staticmethod
-    def camera_of(ray_bundle):
-        """SU:148-155: one camera per call; rotation and origin come from ray 0."""
+    def camera_of(ray_bundle, with_near_far=False):
+        """SU:148-155: one camera per call; rotation and origin come from ray 0 (and near / far, SU:154-155).
+        One device->host transfer for all of them."""
         rot = ray_bundle.metadata["camrotc2w"]
         rot = rot[0].view(3, 3) if rot.shape[0] != 3 else rot
-        return ray_bundle.origins[0].detach().float().cpu().numpy(), rot.detach().float().cpu().numpy()
+        parts = [ray_bundle.origins[0].detach().float().reshape(-1), rot.detach().float().reshape(-1)]
+        if with_near_far:
+            parts += [ray_bundle.nears[0].detach().float().reshape(-1)[:1], ray_bundle.fars[0].detach().float().reshape(-1)[:1]]
+        h = torch.cat(parts).cpu().numpy()
+        if with_near_far:
+            return h[:3].copy(), h[3:12].reshape(3, 3).copy(), float(h[12]), float(h[13])
+        return h[:3].copy(), h[3:12].reshape(3, 3).copy()
 
     def coarse_t(self, R, near, far, jitter, generator=None):
         """t mid-points of near_far_linear_ray_generation (RM:312-329): (D,) when jitter == 0 else (R,D)."""
@@ -228,11 +235,12 @@ class NeuralPoints(nn.Module):
     def query(self, ray_bundle, jitter=None, generator=None, want_stats=False, near=None, far=None):
         """Rows G0/G2/Q on the cached grid.  Returns (QueryResult, origin, R_c2w)."""
         cfg = self.config
-        origin, R_c2w = self.camera_of(ray_bundle)
+        if near is None:
+            origin, R_c2w, near, far = self.camera_of(ray_bundle, with_near_far=True)
+        else:
+            origin, R_c2w = self.camera_of(ray_bundle)
         dirs = ray_bundle.directions.to(self.device).float().contiguous()
         R = dirs.shape[0]
-        if near is None:
-            near, far = float(ray_bundle.nears[0]), float(ray_bundle.fars[0])           # SU:154-155
         jitter = cfg.jitter if jitter is None else jitter
         if jitter and generator is None:
             # jittered t generated inside the selection kernel (Philox keyed by a per-call seed): no (R,D) tensor at all
@@ -357,6 +365,13 @@ class PointNerf(nn.Module):
 
     def get_outputs(self, ray_bundle, generator=None):
         """SM:263-399."""
+        native.pin_stream()
+        try:
+            return self._get_outputs(ray_bundle, generator)
+        finally:
+            native.unpin_stream()
+
+    def _get_outputs(self, ray_bundle, generator=None):
         c = self.config
         npnts = self.neural_points
         q, origin, R_c2w, dirs = npnts.query(ray_bundle, generator=generator)

@@ -50,9 +50,83 @@ def field_forward_tc(cfg, q, dirs, pts, mlp, wpack, ids, S: int):
     return sigma, rgb
 
 
+class _RenderTC(torch.autograd.Function):
+    """Tensor-core training path: fused per-neighbour networks (operands kept), fp32 colour network, step length + compositing
+    as one autograd node; backward = composite backward + bf16 tcgen05 dgrad / wgrad GEMMs + scatter into the point tensors."""
+
+    @staticmethod
+    def forward(ctx, cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, *mlp_params):
+        lib = _lib.load()
+        wpack, mlp, params = packed_weights(mlp_params)
+        pts = make_points(xyz.detach(), embed.detach(), color.detach(), dirn.detach(), conf.detach(), Rw2c)
+        ids, n_dev = native.compact_samples(q.sample_valid)
+        S = int(n_dev.item())
+        R, SR, K = q.sample_pidx.shape
+        dev = dirs.device
+        sigma = torch.zeros((R, SR), dtype=torch.float32, device=dev)
+        rgb = torch.zeros((R, SR, 3), dtype=torch.float32, device=dev)
+        ws_bytes = lib.pnerf_field_tc_train_workspace_bytes(S, K)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+        with Timers.span("field"):
+            check(lib.pnerf_field_forward_tc_train(C.byref(pts), C.byref(cfg["camera"]), C.byref(mlp), _ptr(wpack), C.byref(cfg["mode"]),
+                                                   _ptr(dirs), _ptr(q.sample_loc), _ptr(q.sample_pidx), _ptr(ids), S, SR, K,
+                                                   _ptr(sigma), _ptr(rgb), _ptr(ws), ws_bytes, _stream()), "pnerf_field_forward_tc_train")
+        LAUNCHES["n"] += 7
+        out = native.composite_forward(cfg, q, sigma, rgb)
+        ctx.cfg, ctx.q, ctx.S, ctx.ids, ctx.ws = cfg, q, S, ids, ws
+        ctx.keep = (dirs, xyz, Rw2c, embed, color, dirn, conf, params, mlp, sigma, rgb)
+        ctx.shapes = [p.shape for p in mlp_params]
+        cfg["last"] = {"sigma": sigma, "rgb": rgb, "n_samples": S}
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        native.pin_stream()
+        try:
+            return _RenderTC._backward(ctx, d_out)
+        finally:
+            native.unpin_stream()
+
+    @staticmethod
+    def _backward(ctx, d_out):
+        lib = _lib.load()
+        cfg, q, S, ids, ws = ctx.cfg, ctx.q, ctx.S, ctx.ids, ctx.ws
+        dirs, xyz, Rw2c, embed, color, dirn, conf, params, mlp, sigma, rgb = ctx.keep
+        R, SR, K = q.sample_pidx.shape
+        dev = dirs.device
+        mode, cam = cfg["mode"], cfg["camera"]
+        d_out = d_out.contiguous().float()
+        d_sigma = torch.empty((R, SR), dtype=torch.float32, device=dev)
+        d_rgb = torch.empty((R, SR, 3), dtype=torch.float32, device=dev)
+        check(lib.pnerf_composite_backward(C.byref(cam), C.byref(mode), _ptr(q.sample_loc), _ptr(q.sample_valid), _ptr(sigma),
+                                           _ptr(rgb), _ptr(d_out), R, SR, _ptr(d_sigma), _ptr(d_rgb), _stream()),
+              "pnerf_composite_backward")
+        need = ctx.needs_input_grad
+        g_embed = torch.zeros_like(embed) if need[5] else None
+        g_color = torch.zeros_like(color) if need[6] else None
+        g_dir = torch.zeros_like(dirn) if need[7] else None
+        g_conf = torch.zeros_like(conf) if (need[8] and mode.weight_conf) else None
+        names = [n for _, w, b in MLP_PARAM_NAMES for n in (w, b)]
+        flat = torch.zeros(sum(p.numel() for p in params.values()), dtype=torch.float32, device=dev)   # one memset for all 18 tensors
+        grads, o = {}, 0
+        for n in names:
+            grads[n] = flat[o:o + params[n].numel()].view(params[n].shape)
+            o += params[n].numel()
+        pts = make_points(xyz.detach(), embed.detach(), color.detach(), dirn.detach(), conf.detach(), Rw2c)
+        gm = make_mlp(grads, _lib.MlpGrad)
+        with Timers.span("field_bwd"):
+            check(lib.pnerf_field_backward_tc(C.byref(pts), C.byref(cam), C.byref(mlp), C.byref(mode), _ptr(dirs), _ptr(q.sample_loc),
+                                              _ptr(q.sample_pidx), _ptr(ids), S, SR, K, _ptr(d_sigma), _ptr(d_rgb), _ptr(g_embed),
+                                              _ptr(g_color), _ptr(g_dir), _ptr(g_conf), C.byref(gm), _ptr(ws), ws.numel(), _stream()),
+                  "pnerf_field_backward_tc")
+        LAUNCHES["n"] += 22
+        mlp_grads = [grads[n].reshape(s) for n, s in zip(names, ctx.shapes)]
+        return (None, None, None, None, None, g_embed, g_color, g_dir, g_conf, *mlp_grads)
+
+
 def render_tc(cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, mlp_params):
     if torch.is_grad_enabled() and any(t.requires_grad for t in (embed, color, dirn, conf, *mlp_params)):
-        raise NotImplementedError("the tensor-core path is forward-only so far; train with PointNerfConfig(precision='fp32')")
+        return _RenderTC.apply(cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, *mlp_params)
     wpack, mlp, _ = packed_weights(mlp_params)
     pts = make_points(xyz.detach(), embed.detach(), color.detach(), dirn.detach(), conf.detach(), Rw2c)
     ids, n_dev = native.compact_samples(q.sample_valid)

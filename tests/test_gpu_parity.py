@@ -160,7 +160,7 @@ def test_edge_cases_empty_and_all_miss():
 
 
 # ------------------------------------------------------------------------------------------------ field + compositing
-def _oracle_render(cloud, cam, pix, W, pidx, loc, hit, SR, mode, training=True):
+def _oracle_render(cloud, cam, pix, W, pidx, loc, hit, SR, mode, training=True, bf16=False):
     cp, cl, cm = gq.compact_rays(pidx, loc, hit)
     pts = {"xyz": torch.from_numpy(cloud.xyz), "Rw2c": torch.from_numpy(cloud.Rw2c)}
     for k in ("embed", "color", "dir", "conf"):
@@ -169,7 +169,7 @@ def _oracle_render(cloud, cam, pix, W, pidx, loc, hit, SR, mode, training=True):
         v.requires_grad_(True)
         v.grad = None
     out = of.render(pts, W, torch.from_numpy(cam.origin), torch.from_numpy(cam.rays(pix)), torch.from_numpy(cam.R_c2w), cp, cl, cm,
-                    0.004, SR, mode=mode, training=training)
+                    0.004, SR, mode=mode, training=training, bf16=bf16)
     return out, pts, cm
 
 

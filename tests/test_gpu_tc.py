@@ -66,8 +66,57 @@ def test_tc_full_image_chunks_agree_with_fp32_kernels():
     assert float((ca - cb).abs().max()) <= 2e-2
 
 
-def test_tc_training_mode_is_refused_loudly():
-    s, cloud, cam, pix = _scene("tinyP")
-    m = _make_model(cloud, "bf16", "plugin", SR=16, K=4, P=3).train()
-    with pytest.raises(NotImplementedError):
-        m.get_outputs(_bundle(cam, pix))
+@pytest.mark.parametrize("flow,K", [("plugin", 8), ("original", 8), ("plugin", 16)])
+def test_tc_training_forward_backward_matches_fp32_autograd(flow, K):
+    """Tensor-core training path (operands kept by the fused forward; bf16 tcgen05 dgrad / wgrad GEMMs) against torch autograd
+    through the oracle evaluated at the same bf16 rounding points as the forward kernel (oracle.field bf16=True: fp32
+    accumulation, straight-through gradients) -- so LeakyReLU units sit on the same side of zero in both -- and, for the
+    weight gradients (sums over ~1e5 rows), also against the pure fp32 oracle.  Stated bf16 tolerances, as (max-norm error /
+    largest entry, cosine similarity): MLP weight / bias gradients 2.5e-2, >= 0.99998 (same rounding points) and 6e-2, >= 0.999
+    (pure fp32 oracle); neural-point gradients (an entry sums one or a few rows, each carrying the bf16 rounding of four
+    chained dgrad GEMMs) 8e-2, >= 0.9995."""
+    name = "config1" if K == 8 else "k16_5cube"
+    s, cloud, cam, pix = _scene(name)
+    pix = pix[:384]
+    SR = 24
+    W = of.FieldWeights.random(seed=7, scale=1.6)
+    _, _, _, pidx_o, loc_o, mask_o, hit_o, _ = _oracle_query(cloud.xyz, cam, pix, SR, s["K"], s["P"], s["ks"])
+    from test_gpu_parity import _oracle_render
+    gt = torch.rand((len(pix), 3), generator=torch.Generator().manual_seed(1))
+    out32, _, cm = _oracle_render(cloud, cam, pix, W, pidx_o, loc_o, hit_o, SR, flow)
+    l32 = of.loss(out32["coarse_raycolor"], cm, gt, out32["conf_coefficient"])
+    (l32["ray_masked_coarse_raycolor_loss"] + l32["conf_coefficient_loss"]).backward()
+    w32 = {k: v.grad.clone() for k, v in W.p.items()}
+    out_o, pts_o, cm = _oracle_render(cloud, cam, pix, W, pidx_o, loc_o, hit_o, SR, flow, bf16=True)
+    model = _make_model(cloud, "bf16", flow, SR=SR, K=s["K"], P=s["P"], ks=s["ks"], weights=W)
+    model.train()
+    out = model.get_outputs(_bundle(cam, pix))
+    np.testing.assert_array_equal(out["ray_mask"].cpu().numpy(), cm)
+    C = out["coarse_raycolor"].detach().cpu().numpy()
+    assert np.abs(C - out32["coarse_raycolor"].detach().numpy()).max() <= 2e-2
+    assert np.abs(C - out_o["coarse_raycolor"].detach().numpy()).max() <= 2e-3
+    lo = of.loss(out_o["coarse_raycolor"], cm, gt, out_o["conf_coefficient"])
+    (lo["ray_masked_coarse_raycolor_loss"] + lo["conf_coefficient_loss"]).backward()
+    ld = model.get_loss_dict(out, {"image": gt.cuda()})
+    (ld["ray_masked_coarse_raycolor_loss"] + ld["conf_coefficient_loss"]).backward()
+    torch.cuda.synchronize()
+
+    bad = []
+
+    def close(got, ref, what, tol, min_cos):
+        scale = np.abs(ref).max()
+        assert scale > 0, what
+        err = np.abs(got - ref).max() / scale
+        cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+        print(f"{what}: max err / max |g| = {err:.3e}, cos = {cos:.6f}")
+        if not (err <= tol and cos >= min_cos):
+            bad.append((what, float(err), cos))
+
+    npnts = model.neural_points
+    for nm, p in (("embed", npnts.points_embeding), ("color", npnts.points_color), ("dir", npnts.points_dir), ("conf", npnts.points_conf)):
+        close(p.grad[0].cpu().numpy(), pts_o[nm].grad.numpy(), nm, 8e-2, 0.9995)
+    own = dict(model.named_parameters())
+    for k, v in W.p.items():
+        close(own[k].grad.cpu().numpy(), v.grad.numpy(), k, 2.5e-2, 0.99998)
+        close(own[k].grad.cpu().numpy(), w32[k].numpy(), k + " (vs fp32 oracle)", 6e-2, 0.999)
+    assert not bad, bad
