@@ -9,18 +9,18 @@
 // of A and only HALF of every weight chunk (its 128 of the 256 output features), so the L2 -> SM weight stream -- the
 // bound of the single-CTA version (557 KB per 128-row tile against ~43 B/clk/SM of L2) -- is halved per SM.
 //   tile      = 128 rows = (128/KP) consecutive valid samples x KP neighbour slots (KP = 8, 16 or 32 >= K)
-//   warps 0-3 : encoder.  Thread = row: gathers the point (xyz, 32-d embedding, colour, dir, conf), computes the
+//   warps 0-7 : encoder, two threads per row (each half of the embedding; dists / weights+extras): gathers the point (xyz, 32-d embedding, colour, dir, conf), computes the
 //               relative position in world and perspective space, the inverse-distance weight, the 284-wide encoded
 //               input (double-angle recurrences from one sincos per input) and writes it as the bf16 A operand of
 //               layer 1 straight into shared memory (K-slab layout, see umma.cuh).  Nothing encoded touches HBM.
-//   warps 4-11 / 12-19 : epilogue group of slot 0 / 1, two warps per 32 TMEM lanes (one per 128-column half: the roles
+//   warps 8-15 / 16-23 : epilogue group of slot 0 / 1, two warps per 32 TMEM lanes (one per 128-column half: the roles
 //               are latency-bound, so a second warp per lane quarter nearly halves an epilogue).  Thread = row = TMEM
 //               lane: tcgen05.ld the fp32 accumulator, bias + LeakyReLU, bf16 pack, write the next layer's A operand in
 //               place; after layer 4 the density head (in-thread dot, halves combined through shared memory), the
 //               weight w_k and the sum over the KP neighbour lanes (register butterfly).
-//   warp 20   : weight producer: streams this CTA's half of the four 256-wide layers (bf16, pre-packed K-slabs, L2
+//   warp 24   : weight producer: streams this CTA's half of the four 256-wide layers (bf16, pre-packed K-slabs, L2
 //               resident) as 8 KB half-chunks through an 8-stage ring with cp.async.bulk + mbarrier complete_tx.
-//   warp 21   : leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 for slot 0 / slot 1 alternately,
+//   warp 25   : leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 for slot 0 / slot 1 alternately,
 //               so one slot's epilogue overlaps the other slot's MMAs; multicast tcgen05.commit releases ring stages
 //               and publishes accumulators in both CTAs.  Peer CTA: relay -- forwards "my half-chunk has landed" to
 //               the leader.  Barriers the issuer waits on live in the leader (remote arrivals from the peer).
@@ -40,13 +40,23 @@ constexpr int KIN_PAD = 288;                     // 284 (layer 1) and 263 (layer
 constexpr int A_BYTES = (KIN_PAD / 8) * SLAB;    // 73728
 // Weight stream.  A bulk copy costs ~240 clk of engine time per SM whatever its size (measured, tools/tc_microbench.py:
 // 4, 8 and 16 KB copies all run at one per 235-245 clk with two issuing lanes, one per ~420 clk with a single lane), so
-// the stream is sized in few, large copies: a chunk is 64 k-columns of a layer, stored as two N-halves of 16 KB (one per
-// CTA of the pair); the 288-wide layers end with a half-size chunk (32 k-columns, 8 KB per CTA).
-constexpr int CHUNK_K = 64;
-constexpr int CHUNK_BYTES = CHUNK_K * HID * 2;   // 32768 for the pair
-constexpr int HALF_BYTES = CHUNK_BYTES / 2;      // 16384: what one CTA loads per full chunk: 8 slabs x 128 output features
+// the stream is sized in few, large copies: a chunk is 48 k-columns of a layer, stored as two N-halves of 12 KB (one per
+// CTA of the pair); the 256-wide layers end with a 16-column chunk.  Chunks travel in groups of two (one per issuing lane),
+// a ring stage = a group, released by ONE tcgen05.commit (a commit costs ~120 clk of tensor-pipe time); three groups in flight.
+constexpr int CHUNK_SLABS = 6;
+constexpr int CHUNK_K = CHUNK_SLABS * 8;
+constexpr int CHUNK_BYTES = CHUNK_K * HID * 2;   // 24576 for the pair
+constexpr int HALF_BYTES = CHUNK_BYTES / 2;      // 12288: what one CTA loads per full chunk: 6 slabs x 128 output features
+constexpr int NGRP = 3;
 constexpr int N_UNITS = 34;                      // 32-k units of 16 KB in the packed buffer: 9 + 8 + 9 + 8
-constexpr int NT = 704;                          // 4 encoder + 2 x 8 epilogue + producer + issuer warps
+// Warp budget.  Measured (render bench, field kernels): ENC_PARTS 1 / EPW 8 (704 threads, 80 registers): 16.6 ms; ENC_PARTS 2 /
+// EPW 8 (832 threads, 72 registers, spills): 17.5 ms although a tile encodes in 4.5 k instead of 7.4 k clk; ENC_PARTS 2 / EPW 4:
+// 19.3 ms.  More warps do not shorten the epilogues -- the roles contend for issue slots in bursts -- so instructions, not
+// warps, are what the next version has to cut.
+constexpr int ENC_PARTS = 1;                     // threads per row in the encoder: 1 (4 warps) or 2 (8 warps)
+constexpr int EPW = 8;                           // epilogue warps per slot: 4 (a warp drains all 256 columns of its 32 lanes) or 8 (128 each)
+constexpr int ENCW = 4 * ENC_PARTS;
+constexpr int NT = (ENCW + 2 * EPW + 2) * 32;    // encoder + 2 x EPW epilogue + producer + issuer warps
 constexpr int MAX_SPT = 16;                      // samples per tile at KP = 8
 
 // colour network
@@ -58,20 +68,21 @@ constexpr int WPACK_BYTES = WPACK_FIELD_BYTES + C1_BYTES + 2 * C2_BYTES;   // 69
 
 struct Cam { float o[3]; float Rc[9]; float Rw[9]; };
 
-struct Meta {                       // per (slot, tile parity): written by the encoder, read by the slot's epilogue group
+struct Meta {                       // per (slot, tile parity): written by the encoder, read by the slot's aggregation epilogue
     float w[ROWS];                  // aggregation weight of the row (0 for masked rows)
-    float dot_hi[ROWS];             // density-head partial dot of columns 128..255 (upper-half epilogue warp -> lower-half warp)
-    uint4 extras[ROWS];             // bf16 x 8: colour 3, dir_r - v 3, <dir_r, v> 1, 0   (layer 3 inputs 256..263)
     int slot_id[MAX_SPT];           // output slot (r*SR+s) of each sample of the tile, -1 past the end
+};
+struct SlotScratch {                // per slot: lifetimes end before the slot's next tile needs them
+    uint4 extras[ROWS];             // encoder -> layer-2 epilogue.  bf16 x 8: colour 3, dir_r - v 3, <dir_r, v> 1, 0 (layer 3 inputs 256..263)
+    float dot_hi[ROWS];             // density-head partial dot of columns 128..255 (upper-half epilogue warp -> lower-half warp)
 };
 
 struct Smem {
     uint8_t A[2][A_BYTES];
-    uint8_t W[2][2][HALF_BYTES];        // two groups in flight, a group = up to two 64-k chunks (this CTA's N-half)
-    float bias[4][HID];
-    float wa[HID];
+    uint8_t W[NGRP][2][HALF_BYTES];     // three groups in flight, a group = two 48-k chunks (this CTA's N-half)
     Meta meta[2][2];
-    uint64_t w_full[2], w_empty[2], w_peer[2];
+    SlotScratch scratch[2];
+    uint64_t w_full[NGRP], w_empty[NGRP], w_peer[NGRP];
     uint64_t a_ready[2], acc_full[2], acc_empty[2], a_free[2];
     uint32_t tmem_base;
 };
@@ -154,12 +165,15 @@ __device__ __forceinline__ void load_ids(const FieldParams& p, int tile, int row
     }
 }
 __device__ __forceinline__ void prefetch_l2(const void* a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
-__device__ __forceinline__ void prefetch_point(const FieldParams& p, int pidx) {
+__device__ __forceinline__ void prefetch_point(const FieldParams& p, int pidx, int part) {
     if (pidx < 0) return;
-    prefetch_l2(p.embed + (int64_t)pidx * 32);
-    prefetch_l2(p.xyz + 3 * (int64_t)pidx);
-    prefetch_l2(p.color + 3 * (int64_t)pidx);
-    prefetch_l2(p.dir + 3 * (int64_t)pidx);
+    if (part == 0) {
+        prefetch_l2(p.embed + (int64_t)pidx * 32);
+        prefetch_l2(p.xyz + 3 * (int64_t)pidx);
+    } else {
+        prefetch_l2(p.color + 3 * (int64_t)pidx);
+        prefetch_l2(p.dir + 3 * (int64_t)pidx);
+    }
 }
 
 // A row-owning thread's view of a 128-row operand tile: slab j of the row lives at [j * SLAB + row * 16].  With SAVE the same
@@ -173,77 +187,91 @@ struct RowSink {
     }
 };
 
-template <int KP, bool SAVE>
-__device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int pidx, uint8_t* Abuf, uint8_t* gsave, Meta& meta, int row) {
+// Two threads per row: PART 0 encodes embedding dims 0..15 (raw -> slabs 0,1; PE -> slabs 4..15) and PE(dists) (slabs 28..35),
+// PART 1 encodes embedding dims 16..31 (slabs 2,3 and 16..27), the aggregation weight, the layer-3 extras and the tile metadata.
+// Both recompute the (cheap) geometry.  The encoder sits on the critical path at every tile boundary -- a slot's A buffer is only
+// free once its layer-4 MMAs are done -- so its latency, not its throughput, is what the split buys.
+template <int KP, bool SAVE, int PART>
+__device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int pidx, uint8_t* Abuf, uint8_t* gsave, Meta& meta,
+                                            SlotScratch& scr, int row) {
     const int k = row % KP;
-    if (k == 0) meta.slot_id[row / KP] = slot;
+    if (PART == 1 && k == 0) meta.slot_id[row / KP] = slot;
     const RowSink<SAVE> A{reinterpret_cast<uint4*>(Abuf + row * 16), reinterpret_cast<uint4*>(gsave + row * 16)};
     float wraw = 0.f, cc = 1.f;
     float ex[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (pidx >= 0) {
         const float sx = __ldg(p.sample_loc + 3 * (int64_t)slot), sy = __ldg(p.sample_loc + 3 * (int64_t)slot + 1),
                     sz = __ldg(p.sample_loc + 3 * (int64_t)slot + 2);
-        const int ray = slot / p.SR;
-        const float rd[3] = {__ldg(p.dirs + 3 * (int64_t)ray), __ldg(p.dirs + 3 * (int64_t)ray + 1), __ldg(p.dirs + 3 * (int64_t)ray + 2)};
         const float X = __ldg(p.xyz + 3 * (int64_t)pidx), Y = __ldg(p.xyz + 3 * (int64_t)pidx + 1), Z = __ldg(p.xyz + 3 * (int64_t)pidx + 2);
-        const float4* e4 = reinterpret_cast<const float4*>(p.embed + (int64_t)pidx * 32);
-        float e[32];
+        const float4* e4 = reinterpret_cast<const float4*>(p.embed + (int64_t)pidx * 32 + 16 * PART);
+        float e[16];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
+        for (int j = 0; j < 4; j++) {
             const float4 t = __ldg(e4 + j);
             e[4 * j] = t.x; e[4 * j + 1] = t.y; e[4 * j + 2] = t.z; e[4 * j + 3] = t.w;
         }
-        const float col[3] = {__ldg(p.color + 3 * (int64_t)pidx), __ldg(p.color + 3 * (int64_t)pidx + 1), __ldg(p.color + 3 * (int64_t)pidx + 2)};
-        const float dd[3] = {__ldg(p.dir + 3 * (int64_t)pidx), __ldg(p.dir + 3 * (int64_t)pidx + 1), __ldg(p.dir + 3 * (int64_t)pidx + 2)};
-        if (p.weight_conf) cc = fminf(fmaxf(__ldg(p.conf + pidx), 1e-4f), 1.f);                // PA:740-742
-        // geometry (SM:273-281)
-        float spx, spy, spz, ppx, ppy, ppz;
-        to_pers(p.cam, sx, sy, sz, spx, spy, spz);
-        to_pers(p.cam, X, Y, Z, ppx, ppy, ppz);
         float d[6];
         d[0] = X - sx; d[1] = Y - sy; d[2] = Z - sz;
-        d[3] = ppx * ppz - spx * spz; d[4] = ppy * ppz - spy * spz; d[5] = ppz - spz;
-        wraw = 1.f / fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-6f);              // SM:471-474
-        float d3[3];
-        rot_w2c(p.cam, d, d3);                                                                  // SM:312
-        d[0] = d3[0]; d[1] = d3[1]; d[2] = d3[2];
-        float v[3], dr[3];
-        rot_w2c(p.cam, rd, v);                                                                  // SM:303-304
-        rot_w2c(p.cam, dd, dr);                                                                 // SM:330
-        ex[0] = col[0]; ex[1] = col[1]; ex[2] = col[2];
-        ex[3] = dr[0] - v[0]; ex[4] = dr[1] - v[1]; ex[5] = dr[2] - v[2];
-        ex[6] = dr[0] * v[0] + dr[1] * v[1] + dr[2] * v[2];                                     // SM:334
-        // layer-1 input [feat 32 | PE(feat, F=3) 192 | PE(dists6, F=5) 60 | 0 x 4]
+        // this part's half of [feat 32 | PE(feat, F=3) 192]
 #pragma unroll
-        for (int j = 0; j < 4; j++) A.put(j, pack8(e + 8 * j));
+        for (int j = 0; j < 2; j++) A.put(2 * PART + j, pack8(e + 8 * j));
 #pragma unroll
-        for (int g = 0; g < 8; g++) {            // 4 embedding dims -> 24 values -> slabs 4+3g .. 4+3g+2
+        for (int g = 0; g < 4; g++) {            // 4 embedding dims -> 24 values -> 3 slabs
             float t[24];
 #pragma unroll
             for (int c = 0; c < 4; c++) pe<3>(e[4 * g + c], t + 6 * c);
 #pragma unroll
-            for (int j = 0; j < 3; j++) A.put(4 + 3 * g + j, pack8(t + 8 * j));
+            for (int j = 0; j < 3; j++) A.put(4 + 12 * PART + 3 * g + j, pack8(t + 8 * j));
         }
-        {
+        if (PART == 0) {
+            // geometry (SM:273-281) and PE(dists6, F=5) 60 | 0 x 4
+            float spx, spy, spz, ppx, ppy, ppz;
+            to_pers(p.cam, sx, sy, sz, spx, spy, spz);
+            to_pers(p.cam, X, Y, Z, ppx, ppy, ppz);
+            d[3] = ppx * ppz - spx * spz; d[4] = ppy * ppz - spy * spz; d[5] = ppz - spz;
+            float d3[3];
+            rot_w2c(p.cam, d, d3);                                                              // SM:312
+            d[0] = d3[0]; d[1] = d3[1]; d[2] = d3[2];
             float t[64];
 #pragma unroll
             for (int c = 0; c < 6; c++) pe<5>(d[c], t + 10 * c);
             t[60] = t[61] = t[62] = t[63] = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; j++) A.put(28 + j, pack8(t + 8 * j));
+        } else {
+            wraw = 1.f / fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-6f);          // SM:471-474
+            const int ray = slot / p.SR;
+            const float rd[3] = {__ldg(p.dirs + 3 * (int64_t)ray), __ldg(p.dirs + 3 * (int64_t)ray + 1), __ldg(p.dirs + 3 * (int64_t)ray + 2)};
+            const float col[3] = {__ldg(p.color + 3 * (int64_t)pidx), __ldg(p.color + 3 * (int64_t)pidx + 1), __ldg(p.color + 3 * (int64_t)pidx + 2)};
+            const float dd[3] = {__ldg(p.dir + 3 * (int64_t)pidx), __ldg(p.dir + 3 * (int64_t)pidx + 1), __ldg(p.dir + 3 * (int64_t)pidx + 2)};
+            if (p.weight_conf) cc = fminf(fmaxf(__ldg(p.conf + pidx), 1e-4f), 1.f);            // PA:740-742
+            float v[3], dr[3];
+            rot_w2c(p.cam, rd, v);                                                              // SM:303-304
+            rot_w2c(p.cam, dd, dr);                                                             // SM:330
+            ex[0] = col[0]; ex[1] = col[1]; ex[2] = col[2];
+            ex[3] = dr[0] - v[0]; ex[4] = dr[1] - v[1]; ex[5] = dr[2] - v[2];
+            ex[6] = dr[0] * v[0] + dr[1] * v[1] + dr[2] * v[2];                                 // SM:334
         }
     } else {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int j = 0; j < KIN_PAD / 8; j++) A.put(j, z);
-    }
-    float wsum = wraw;                            // SM:286: normalise over the sample's neighbours
+        for (int j = 0; j < 2; j++) A.put(2 * PART + j, z);
 #pragma unroll
-    for (int o = KP / 2; o; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-    float w = wraw / fmaxf(wsum, 1e-8f);
-    if (p.weight_conf) w *= cc;                   // PA:826 (original flow only)
-    meta.w[row] = pidx >= 0 ? w : 0.f;
-    meta.extras[row] = pack8(ex);
+        for (int j = 0; j < 12; j++) A.put(4 + 12 * PART + j, z);
+        if (PART == 0) {
+#pragma unroll
+            for (int j = 28; j < KIN_PAD / 8; j++) A.put(j, z);
+        }
+    }
+    if (PART == 1) {
+        float wsum = wraw;                        // SM:286: normalise over the sample's neighbours
+#pragma unroll
+        for (int o = KP / 2; o; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        float w = wraw / fmaxf(wsum, 1e-8f);
+        if (p.weight_conf) w *= cc;               // PA:826 (original flow only)
+        meta.w[row] = pidx >= 0 ? w : 0.f;
+        scr.extras[row] = pack8(ex);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- epilogues
@@ -254,7 +282,7 @@ template <bool SAVE>
 __device__ __forceinline__ void epilogue_chunk_store(float (&v)[32], const float* __restrict__ bias, float slope, const RowSink<SAVE>& A, int c0) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));   // same address in every lane: one L1 transaction
         float x;
         x = v[j] + b.x; v[j] = fmaxf(x, x * slope);
         x = v[j + 1] + b.y; v[j + 1] = fmaxf(x, x * slope);
@@ -312,8 +340,8 @@ __device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)
     const int gl = lane % KP;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(bias + c0 + j);
-        const float4 a = *reinterpret_cast<const float4*>(wa + c0 + j);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+        const float4 a = __ldg(reinterpret_cast<const float4*>(wa + c0 + j));
         float x;
         x = v[j] + b.x; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.x, dot); v[j] = x;
         x = v[j + 1] + b.y; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.y, dot); v[j + 1] = x;
@@ -342,7 +370,8 @@ __device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)
 
 template <int KP, bool SAVE>
 __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_t tacc_lane, const float* __restrict__ bias,
-                                                   const float* __restrict__ wa, Meta& meta, int tile, int row, int half, int bar_id) {
+                                                   const float* __restrict__ wa, Meta& meta, SlotScratch& scr, int tile, int row, int half,
+                                                   int bar_id) {
     uint4* gh4 = SAVE ? reinterpret_cast<uint4*>(p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)SAVE_H4 * SLAB + row * 16) : nullptr;
     constexpr int SPT = ROWS / KP;
     const int lane = threadIdx.x & 31, gl = lane % KP;
@@ -351,25 +380,31 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
     const float w = meta.w[row];
     const int slot = meta.slot_id[sl];
     float dot = 0.f;
-    const int cbeg = half * (HID / 2);
-    float va[32], vb[32];
-    tmem_ld32(tacc_lane + cbeg, va);
-    tmem_ld_wait();
-    tmem_ld32(tacc_lane + cbeg + 32, vb);
-    aggregate_chunk<KP, SAVE>(p, va, bias, wa, w, dot, slot, si, cbeg, lane, gh4);
-    tmem_ld_wait();
-    tmem_ld32(tacc_lane + cbeg + 64, va);
-    aggregate_chunk<KP, SAVE>(p, vb, bias, wa, w, dot, slot, si, cbeg + 32, lane, gh4);
-    tmem_ld_wait();
-    tmem_ld32(tacc_lane + cbeg + 96, vb);
-    aggregate_chunk<KP, SAVE>(p, va, bias, wa, w, dot, slot, si, cbeg + 64, lane, gh4);
-    tmem_ld_wait();
-    aggregate_chunk<KP, SAVE>(p, vb, bias, wa, w, dot, slot, si, cbeg + 96, lane, gh4);
+#pragma unroll 1
+    for (int cbeg = (EPW == 8 ? half * (HID / 2) : 0); cbeg < (EPW == 8 ? (half + 1) * (HID / 2) : HID); cbeg += HID / 2) {
+        float va[32], vb[32];
+        tmem_ld32(tacc_lane + cbeg, va);
+        tmem_ld_wait();
+        tmem_ld32(tacc_lane + cbeg + 32, vb);
+        aggregate_chunk<KP, SAVE>(p, va, bias, wa, w, dot, slot, si, cbeg, lane, gh4);
+        tmem_ld_wait();
+        tmem_ld32(tacc_lane + cbeg + 64, va);
+        aggregate_chunk<KP, SAVE>(p, vb, bias, wa, w, dot, slot, si, cbeg + 32, lane, gh4);
+        tmem_ld_wait();
+        tmem_ld32(tacc_lane + cbeg + 96, vb);
+        aggregate_chunk<KP, SAVE>(p, va, bias, wa, w, dot, slot, si, cbeg + 64, lane, gh4);
+        tmem_ld_wait();
+        aggregate_chunk<KP, SAVE>(p, vb, bias, wa, w, dot, slot, si, cbeg + 96, lane, gh4);
+    }
     // combine the two column halves of the density head: the upper-half warp hands its partial dot to the lower-half warp
-    if (half) meta.dot_hi[row] = dot;
-    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-    if (half) return;
-    const float raw = dot + meta.dot_hi[row] + __ldg(p.ba);
+    float dot_other = 0.f;
+    if (EPW == 8) {
+        if (half) scr.dot_hi[row] = dot;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        if (half) return;
+        dot_other = scr.dot_hi[row];
+    }
+    const float raw = dot + dot_other + __ldg(p.ba);
     if (SAVE) { p.save_raw[(int64_t)tile * ROWS + row] = raw; p.save_w[(int64_t)tile * ROWS + row] = w; }
     const float a = p.softplus ? softplus_f(raw - 1.f) : fmaxf(raw, 0.f);   // PA:260-265 / SM:221
     float sg = w * a;
@@ -379,9 +414,11 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
 }
 
 __host__ __device__ constexpr int layer_slabs(int L) { return (L & 1) ? 32 : 36; }     // 8-wide k-slabs of the layer (K = 256 / 288)
-__host__ __device__ constexpr int layer_chunks(int L) { return (L & 1) ? 4 : 5; }      // 64-k chunks, the last of a 288 layer is half
+__host__ __device__ constexpr int layer_chunks(int L) { return (void)L, 6; }            // 48-k chunks: 288 = 6 x 48, 256 = 5 x 48 + 16
 __host__ __device__ constexpr int layer_byte0(int L) { return 16384 * (L == 0 ? 0 : (L == 1 ? 9 : (L == 2 ? 17 : 26))); }
-__host__ __device__ constexpr int chunk_slabs(int L, int c) { return layer_slabs(L) - 8 * c < 8 ? layer_slabs(L) - 8 * c : 8; }
+__host__ __device__ constexpr int chunk_slabs(int L, int c) {
+    return layer_slabs(L) - CHUNK_SLABS * c < CHUNK_SLABS ? layer_slabs(L) - CHUNK_SLABS * c : CHUNK_SLABS;
+}
 
 // The order in which (slot, layer) steps go through the tensor pipe, shared by the weight producer, the MMA issuer and the
 // relay.  Slot s works on this CTA's tiles j = 2*it + s; step q of a slot is layer q & 3 of its tile q >> 2.  Slot 1 runs
@@ -408,18 +445,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
     auto tile_of = [&](int j) { return 2 * (pair + j * n_pairs) + (int)rank; };
 
     if (tid == 0) {
-        for (int i = 0; i < 2; i++) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); mbar_init(&sm.w_peer[i], 1); }
+        for (int i = 0; i < NGRP; i++) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); mbar_init(&sm.w_peer[i], 1); }
         for (int s = 0; s < 2; s++) {
-            // a_ready / acc_empty: one arrival per epilogue warp of the pair (2 CTAs x 8); the 4 encoder warps arrive twice
-            mbar_init(&sm.a_ready[s], 16); mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.acc_empty[s], 16); mbar_init(&sm.a_free[s], 1);
+            // a_ready / acc_empty: one arrival per warp of the pair: 2 CTAs x 8 encoder warps, 2 CTAs x 8 epilogue warps
+            mbar_init(&sm.a_ready[s], 16); mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.acc_empty[s], 2 * EPW); mbar_init(&sm.a_free[s], 1);
         }
         fence_barrier_init();
     }
-    if (warp == 21) tmem_alloc2(&sm.tmem_base, 512);
-    for (int i = tid; i < HID; i += NT) {
-        sm.bias[0][i] = p.b1[i]; sm.bias[1][i] = p.b2[i]; sm.bias[2][i] = p.b3[i]; sm.bias[3][i] = p.b4[i];
-        sm.wa[i] = p.wa[i];
-    }
+    if (warp == ENCW + 2 * EPW + 1) tmem_alloc2(&sm.tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // both CTAs' barriers exist before any remote arrive / multicast commit
@@ -427,32 +460,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
     const uint32_t tmem = sm.tmem_base;
 
     Tracer tr(p.trace, warp, lane);
-    if (warp < 4) {
-        // ===================================================== encoder
+    if (warp < ENCW) {
+        // ===================================================== encoder: ENC_PARTS threads per row (warps 0-3 part 0, warps 4-7 part 1)
+        const int part = warp >> 2, erow = tid & 127;
         uint32_t ph[2] = {0, 0};
         int slot0, pidx0, slot1 = -1, pidx1 = -1;
-        load_ids<KP>(p, tile_of(0), tid, slot0, pidx0);
-        if (n_my > 1) load_ids<KP>(p, tile_of(1), tid, slot1, pidx1);
+        load_ids<KP>(p, tile_of(0), erow, slot0, pidx0);
+        if (n_my > 1) load_ids<KP>(p, tile_of(1), erow, slot1, pidx1);
         for (int j = 0; j < n_my; j++) {
             const int s = j & 1;
             int slot2 = -1, pidx2 = -1;
-            if (j + 2 < n_my) load_ids<KP>(p, tile_of(j + 2), tid, slot2, pidx2);
-            prefetch_point(p, pidx1);
+            if (j + 2 < n_my) load_ids<KP>(p, tile_of(j + 2), erow, slot2, pidx2);
+            if (ENC_PARTS == 1) { prefetch_point(p, pidx1, 0); prefetch_point(p, pidx1, 1); }
+            else prefetch_point(p, pidx1, part);
             if (j >= 2) { mbar_wait(&sm.a_free[s], ph[s]); ph[s] ^= 1; }
             tr.ev(1);
-            encode_tile<KP, SAVE>(p, slot0, pidx0, sm.A[s], SAVE ? p.save + (int64_t)tile_of(j) * SAVE_TILE_BYTES : nullptr,
-                                  sm.meta[s][(j >> 1) & 1], tid);
+            uint8_t* gsave = SAVE ? p.save + (int64_t)tile_of(j) * SAVE_TILE_BYTES : nullptr;
+            if (ENC_PARTS == 1 || part == 0) encode_tile<KP, SAVE, 0>(p, slot0, pidx0, sm.A[s], gsave, sm.meta[s][(j >> 1) & 1], sm.scratch[s], erow);
+            if (ENC_PARTS == 1 || part == 1) encode_tile<KP, SAVE, 1>(p, slot0, pidx0, sm.A[s], gsave, sm.meta[s][(j >> 1) & 1], sm.scratch[s], erow);
             slot0 = slot1; pidx0 = pidx1; slot1 = slot2; pidx1 = pidx2;
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) { mbar_arrive_remote(&sm.a_ready[s], 0); mbar_arrive_remote(&sm.a_ready[s], 0); }
+            if (lane == 0) {
+                for (int i = 0; i < 4 / ENCW + 1; i++) mbar_arrive_remote(&sm.a_ready[s], 0);   // the barrier counts 16 per pair: 2 per warp at ENCW = 4
+            }
             tr.ev(2);
         }
-    } else if (warp < 20) {
+    } else if (warp < ENCW + 2 * EPW) {
         // ===================================================== epilogue group of slot s: warp = lane quarter (warp & 3, the
-        // TMEM lanes a warp may touch) x column half
-        const int s = (warp - 4) >> 3;
-        const int half = ((warp - 4) >> 2) & 1;
+        // TMEM lanes a warp may touch) [x column half when EPW == 8]
+        const int s = (warp - ENCW) / EPW;
+        const int half = EPW == 8 ? ((warp - ENCW) >> 2) & 1 : 0;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t tacc_lane = tmem + (uint32_t)(s * HID) + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t ph = 0;
@@ -467,29 +505,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
                 // layer L's output is the next layer's A operand: H1 (L=0), X3 = [H2 | extras] (L=1), H3 (L=2)
                 uint8_t* gsave = SAVE ? p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)(L == 0 ? SAVE_H1 : (L == 1 ? SAVE_X3 : SAVE_H3)) * SLAB
                                       : nullptr;
-                epilogue_store<SAVE>(tacc_lane, sm.bias[L], p.slope, sm.A[s], gsave, row, half * (HID / 2));
-                if (L == 1 && half) {   // layer-3 input columns 256..287: the 7 per-row extras, then zeros
+                const float* bias = L == 0 ? p.b1 : (L == 1 ? p.b2 : p.b3);
+                if (EPW == 8) {
+                    epilogue_store<SAVE>(tacc_lane, bias, p.slope, sm.A[s], gsave, row, half * (HID / 2));
+                } else {
+                    epilogue_store<SAVE>(tacc_lane, bias, p.slope, sm.A[s], gsave, row, 0);
+                    epilogue_store<SAVE>(tacc_lane, bias, p.slope, sm.A[s], gsave, row, HID / 2);
+                }
+                if (L == 1 && (half || EPW == 4)) {   // layer-3 input columns 256..287: the 7 per-row extras, then zeros
                     const RowSink<SAVE> A{reinterpret_cast<uint4*>(sm.A[s] + row * 16), reinterpret_cast<uint4*>(gsave + row * 16)};
-                    A.put(32, meta.extras[row]);
+                    A.put(32, sm.scratch[s].extras[row]);
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
                     A.put(33, z); A.put(34, z); A.put(35, z);
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_remote(&sm.a_ready[s], 0);
+                if (lane == 0) {
+                    mbar_arrive_remote(&sm.a_ready[s], 0);
+                    if (EPW == 4) mbar_arrive_remote(&sm.a_ready[s], 0);   // the barrier counts 16 = the 8 encoder warps of each CTA
+                }
                 tr.ev(20 + L);
             }
             mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
             tc_fence_after();
             tr.ev(13);
-            epilogue_aggregate<KP, SAVE>(p, tacc_lane, sm.bias[3], sm.wa, meta, tile, row, half, 1 + s * 4 + (warp & 3));
+            epilogue_aggregate<KP, SAVE>(p, tacc_lane, p.b4, p.wa, meta, sm.scratch[s], tile, row, half, 1 + s * 4 + (warp & 3));
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&sm.acc_empty[s], 0);
             tr.ev(23);
         }
-    } else if (warp == 20) {
+    } else if (warp == ENCW + 2 * EPW) {
         // ===================================================== weight producer
         // Two issuing lanes (one lane alone sustains only a copy per ~420 clk): lane e loads chunk e of every group.
         if (lane < 2) {
@@ -497,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
             for_each_step(n_my, [&](int s, int L, int it) {
                 (void)s; (void)it;
                 for (int c0 = 0; c0 < layer_chunks(L); c0 += 2, g++) {
-                    const uint32_t b = g & 1, phase = (g >> 1) & 1;
+                    const uint32_t b = g % NGRP, phase = (g / NGRP) & 1;
                     const int nc = layer_chunks(L) - c0 < 2 ? 1 : 2;
                     mbar_wait(&sm.w_empty[b], phase ^ 1);
                     if (lane == 0) {
@@ -527,7 +574,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
                 const uint32_t tacc = tmem + (uint32_t)(s * HID);
                 const uint32_t a_base = smem_u32(sm.A[s]);
                 for (int c0 = 0; c0 < layer_chunks(L); c0 += 2, g++) {
-                    const uint32_t b = g & 1, phase = (g >> 1) & 1;
+                    const uint32_t b = g % NGRP, phase = (g / NGRP) & 1;
                     const int nc = layer_chunks(L) - c0 < 2 ? 1 : 2;
                     mbar_wait(&sm.w_full[b], phase);
                     mbar_wait_cluster(&sm.w_peer[b], phase);
@@ -537,7 +584,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
                         const uint32_t b_base = smem_u32(sm.W[b][e]);
                         const int nk = chunk_slabs(L, c) >> 1;
                         for (int kk = 0; kk < nk; kk++) {
-                            const uint64_t ad = make_smem_desc(a_base + (uint32_t)((c * 8 + kk * 2) * SLAB), SLAB, 128);
+                            const uint64_t ad = make_smem_desc(a_base + (uint32_t)((c * CHUNK_SLABS + kk * 2) * SLAB), SLAB, 128);
                             const uint64_t bd = make_smem_desc(b_base + (uint32_t)(kk * 2 * (HID / 2) * 16), (HID / 2) * 16, 128);
                             mma_bf16_2cta(tacc, ad, bd, idesc, (uint32_t)((c | kk) > 0));
                         }
@@ -556,8 +603,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
             for_each_step(n_my, [&](int s, int L, int it) {
                 (void)s; (void)it;
                 for (int c0 = 0; c0 < layer_chunks(L); c0 += 2, g++) {
-                    mbar_wait(&sm.w_full[g & 1], (g >> 1) & 1);
-                    mbar_arrive_remote(&sm.w_peer[g & 1], 0);
+                    mbar_wait(&sm.w_full[g % NGRP], (g / NGRP) & 1);
+                    mbar_arrive_remote(&sm.w_peer[g % NGRP], 0);
                 }
             });
         }
@@ -565,7 +612,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // nobody leaves while the peer may still signal it / the pair's MMAs are in flight
-    if (warp == 21) tmem_dealloc2(tmem, 512);
+    if (warp == ENCW + 2 * EPW + 1) tmem_dealloc2(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------- colour network
@@ -727,10 +774,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackJobs jobs, uint8_
         const int k = i % jb.kpad, n = i / jb.kpad;
         const float v = k < jb.in ? jb.w[(int64_t)n * jb.in + k] : 0.f;
         __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst + jb.dst_off);
-        if (jb.split) {   // field layers: 64-k chunks of [N-half 2][k-slab <=8][128 features][8]: a CTA of a pair bulk-copies one half
-            const int ks = k >> 3, h = n >> 7, c = ks >> 3;
-            const int nsl = jb.kpad / 8 - 8 * c < 8 ? jb.kpad / 8 - 8 * c : 8;
-            d[(int64_t)c * 16384 + ((int64_t)h * nsl + (ks & 7)) * 1024 + (n & 127) * 8 + (k & 7)] = __float2bfloat16(v);
+        if (jb.split) {   // field layers: 48-k chunks of [N-half 2][k-slab <=6][128 features][8]: a CTA of a pair bulk-copies one half
+            const int ks = k >> 3, h = n >> 7, c = ks / CHUNK_SLABS;
+            const int nsl = jb.kpad / 8 - CHUNK_SLABS * c < CHUNK_SLABS ? jb.kpad / 8 - CHUNK_SLABS * c : CHUNK_SLABS;
+            d[(int64_t)c * (CHUNK_BYTES / 2) + ((int64_t)h * nsl + (ks - c * CHUNK_SLABS)) * 1024 + (n & 127) * 8 + (k & 7)] = __float2bfloat16(v);
         } else {
             d[((int64_t)(k >> 3) * jb.out + n) * 8 + (k & 7)] = __float2bfloat16(v);
         }
@@ -751,7 +798,7 @@ using namespace pnerf;
 
 static unsigned long long* g_trace = nullptr;
 extern "C" int pnerf_tc_set_trace(void* buf) { g_trace = (unsigned long long*)buf; return PNERF_OK; }
-extern "C" int64_t pnerf_tc_trace_bytes(void) { return (int64_t)24 * TRACE_PER_WARP * 8; }
+extern "C" int64_t pnerf_tc_trace_bytes(void) { return (int64_t)32 * TRACE_PER_WARP * 8; }
 
 extern "C" int64_t pnerf_tc_wpack_bytes(void) { return WPACK_BYTES; }
 

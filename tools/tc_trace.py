@@ -31,8 +31,8 @@ def main():
     model.get_outputs_for_camera_ray_bundle(rb)
     torch.cuda.synchronize()
     lib.pnerf_tc_set_trace(None)
-    t = buf.cpu().numpy().reshape(24, -1)
-    names = {0: "encoder", 4: "epilogue slot0 lo", 8: "epilogue slot0 hi", 12: "epilogue slot1 lo", 21: "mma issuer"}
+    t = buf.cpu().numpy().reshape(32, -1)
+    names = {0: "encoder", 4: "epilogue slot0 lo", 12: "epilogue slot1 lo", 21: "mma issuer"}
     for w, name in names.items():
         cnt = int(t[w, 0])
         ev = t[w, 1:cnt]
