@@ -73,9 +73,11 @@ typedef struct {
  *   t_vals != NULL, t_stride=D  : per-ray t table (R,D)
  * (mul then add, separately rounded, as torch evaluates RM:330).
  * outputs, not compacted over rays:
- *   sample_loc (R,SR,3) zero where empty; sample_cnt (R) = min(#hits, SR); 0 <=> ray not in R'. */
+ *   sample_loc (R,SR,3) zero where empty; sample_cnt (R) = min(#hits, SR); 0 <=> ray not in R'.
+ *   fill_missed = 0 leaves the rows of rays without any hit unwritten (the caller compacts the hit rays with
+ *   pnerf_hit_rays / pnerf_gather_hit_rays and never reads them: 5 of 6 rays of an 800x800 object view). */
 int pnerf_sample_select(const pnerf_grid_view* grid_h, const float* raypos, const float* origin_h,
-                        const float* dirs, const float* t_vals, int t_stride, int R, int D, int SR,
+                        const float* dirs, const float* t_vals, int t_stride, int R, int D, int SR, int fill_missed,
                         float* sample_loc, int* sample_cnt, void* stream);
 /* Same, with the coarse t mid-points of near_far_linear_ray_generation (RM:312-329, called with jitter 0.3 at
  * SU:166) generated in registers: segment j = (edge_{j+1} - edge_j) * (1 + jitter * (U - 0.5)), U = Philox4x32-10
@@ -83,8 +85,14 @@ int pnerf_sample_select(const pnerf_grid_view* grid_h, const float* raypos, cons
  * in distribution, not bit for bit; pnerf_coarse_t writes the very t (R,D) and U (R,D, optional) this kernel uses so
  * that a checker can replay them through the t-table source above. */
 int pnerf_sample_select_jitter(const pnerf_grid_view* grid_h, const float* origin_h, const float* dirs, float near_t,
-                               float far_t, float jitter, uint64_t seed, int R, int D, int SR, float* sample_loc,
-                               int* sample_cnt, void* stream);
+                               float far_t, float jitter, uint64_t seed, int R, int D, int SR, int fill_missed,
+                               float* sample_loc, int* sample_cnt, void* stream);
+/* Hit-ray compaction (R -> R' of the reference's op, CU:381-391): ids of the rays with sample_cnt > 0, ascending, and their
+ * rows of sample_loc / sample_cnt / dirs gathered into compact (R',.) arrays; every later stage then runs on R' rays. */
+int pnerf_hit_rays(const int* sample_cnt, int R, int* ray_index, int* n_rays, void* workspace, int64_t workspace_bytes,
+                   void* stream);
+int pnerf_gather_hit_rays(const int* ray_index, int n_rays, int SR, const float* sample_loc, const int* sample_cnt,
+                          const float* dirs, float* loc_out, int* cnt_out, float* dirs_out, void* stream);
 int pnerf_coarse_t(float near_t, float far_t, float jitter, uint64_t seed, int R, int D, float* t_out, float* u_out,
                    void* stream);
 

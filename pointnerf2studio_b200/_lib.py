@@ -63,9 +63,12 @@ SIGNATURES = {
     "pnerf_grid_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pnerf_sample_select": (C.c_int, [C.POINTER(GridView), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pnerf_sample_select_jitter": (C.c_int, [C.POINTER(GridView), C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
-                                             C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                             C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pnerf_hit_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pnerf_gather_hit_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     "pnerf_coarse_t": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
     "pnerf_query": (C.c_int, [C.POINTER(GridView), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -106,7 +106,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) sample_select_kernel(Frame f, const uint32_t* __restrict__ occ,
                                                              const float* __restrict__ raypos, float ox, float oy, float oz,
                                                              const float* __restrict__ dirs, const float* __restrict__ t_vals,
-                                                             int t_stride, TGen gen, int R, int D, int SR,
+                                                             int t_stride, TGen gen, int R, int D, int SR, int fill_missed,
                                                              float* __restrict__ sample_loc, int* __restrict__ sample_cnt) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(256) sample_select_kernel(Frame f, const uint3
             }
         }
         n = min(n, SR);
-        for (int e = 3 * n + lane; e < 3 * SR; e += 32) loc[e] = 0.f;   // unfilled slots stay (0,0,0) (CU:383)
+        if (n > 0 || fill_missed)
+            for (int e = 3 * n + lane; e < 3 * SR; e += 32) loc[e] = 0.f;   // unfilled slots stay (0,0,0) (CU:383)
         if (lane == 0) sample_cnt[r] = n;
     }
 }
@@ -308,7 +309,7 @@ int ray_warps_grid(int R) {
 using namespace pnerf;
 
 extern "C" int pnerf_sample_select(const pnerf_grid_view* g, const float* raypos, const float* origin_h, const float* dirs,
-                                   const float* t_vals, int t_stride, int R, int D, int SR, float* sample_loc,
+                                   const float* t_vals, int t_stride, int R, int D, int SR, int fill_missed, float* sample_loc,
                                    int* sample_cnt, void* stream) {
     if (!g || R < 0 || D <= 0 || SR <= 0) return PNERF_ERR_ARG;
     if (R == 0) return PNERF_OK;
@@ -319,17 +320,17 @@ extern "C" int pnerf_sample_select(const pnerf_grid_view* g, const float* raypos
     cudaStream_t st = (cudaStream_t)stream;
     if (raypos)
         sample_select_kernel<0><<<ray_warps_grid(R), 256, 0, st>>>(f, g->occ_bits, raypos, 0.f, 0.f, 0.f, nullptr, nullptr, 0, gen, R, D, SR,
-                                                                  sample_loc, sample_cnt);
+                                                                  fill_missed, sample_loc, sample_cnt);
     else
         sample_select_kernel<1><<<ray_warps_grid(R), 256, 0, st>>>(f, g->occ_bits, nullptr, origin_h[0], origin_h[1], origin_h[2], dirs,
-                                                                  t_vals, t_stride, gen, R, D, SR, sample_loc, sample_cnt);
+                                                                  t_vals, t_stride, gen, R, D, SR, fill_missed, sample_loc, sample_cnt);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }
 
 extern "C" int pnerf_sample_select_jitter(const pnerf_grid_view* g, const float* origin_h, const float* dirs, float near, float far,
-                                          float jitter, uint64_t seed, int R, int D, int SR, float* sample_loc, int* sample_cnt,
-                                          void* stream) {
+                                          float jitter, uint64_t seed, int R, int D, int SR, int fill_missed, float* sample_loc,
+                                          int* sample_cnt, void* stream) {
     if (!g || R < 0 || D <= 0 || SR <= 0 || !(far > near)) return PNERF_ERR_ARG;
     if (R == 0) return PNERF_OK;
     if (!sample_loc || !sample_cnt || !g->occ_bits || !origin_h || !dirs) return PNERF_ERR_ARG;
@@ -337,7 +338,7 @@ extern "C" int pnerf_sample_select_jitter(const pnerf_grid_view* g, const float*
     const TGen gen = {near, far, jitter, (uint32_t)seed, (uint32_t)(seed >> 32)};
     sample_select_kernel<2><<<ray_warps_grid(R), 256, 0, (cudaStream_t)stream>>>(f, g->occ_bits, nullptr, origin_h[0], origin_h[1],
                                                                                 origin_h[2], dirs, nullptr, 0, gen, R, D, SR,
-                                                                                sample_loc, sample_cnt);
+                                                                                fill_missed, sample_loc, sample_cnt);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }

@@ -156,10 +156,67 @@ __global__ void gather_rays_kernel(const int* __restrict__ ray_index, int n_rays
     if (e < SR * K) out_pidx[(int64_t)rr * SR * K + e] = pidx[(int64_t)r * SR * K + e];
     else { e -= SR * K; out_loc[(int64_t)rr * SR * 3 + e] = loc[(int64_t)r * SR * 3 + e]; }
 }
+// ---- hit-ray compaction: rays whose sample selection found at least one occupied position (R' of SURVEY.md section 8)
+__global__ void hit_flags_kernel(const int* __restrict__ cnt, int R, int* __restrict__ flag) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) flag[r] = cnt[r] > 0 ? 1 : 0;
+}
+__global__ void scatter_hits_kernel(const int* __restrict__ pos, const int* __restrict__ cnt, int R, int* __restrict__ ray_index,
+                                    int* __restrict__ n_rays) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R && cnt[r] > 0) ray_index[pos[r]] = r;
+    if (r == 0) *n_rays = pos[R];
+}
+// one warp per compact ray: its SR sample positions, its count and its direction
+__global__ void __launch_bounds__(256) gather_hits_kernel(const int* __restrict__ ray_index, int n, int SR, const float* __restrict__ loc,
+                                                           const int* __restrict__ cnt, const float* __restrict__ dirs,
+                                                           float* __restrict__ loc_out, int* __restrict__ cnt_out,
+                                                           float* __restrict__ dirs_out) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const int r = ray_index[i];
+        const float* src = loc + (int64_t)r * SR * 3;
+        float* dst = loc_out + (int64_t)i * SR * 3;
+        for (int e = lane; e < 3 * SR; e += 32) dst[e] = src[e];
+        if (lane == 0) cnt_out[i] = cnt[r];
+        if (lane < 3 && dirs) dirs_out[3 * (int64_t)i + lane] = dirs[3 * (int64_t)r + lane];
+    }
+}
 }  // namespace
 }  // namespace pnerf
 
 using namespace pnerf;
+
+extern "C" int pnerf_hit_rays(const int* sample_cnt, int R, int* ray_index, int* n_rays, void* workspace, int64_t workspace_bytes,
+                              void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (R < 0 || !n_rays) return PNERF_ERR_ARG;
+    if (R == 0) { PNERF_CUDA(cudaMemsetAsync(n_rays, 0, 4, st)); return PNERF_OK; }
+    if (!sample_cnt || !ray_index || !workspace) return PNERF_ERR_ARG;
+    int64_t pos_bytes = align_up(((int64_t)R + 1) * 4, 256);
+    if (workspace_bytes < pos_bytes + scan_workspace_bytes(R)) return PNERF_ERR_WORKSPACE;
+    int* pos = (int*)workspace;
+    hit_flags_kernel<<<(R + 255) / 256, 256, 0, st>>>(sample_cnt, R, pos);
+    PNERF_LAUNCH_CHECK();
+    int rc = exclusive_scan_i32(pos, pos, R, true, (char*)workspace + pos_bytes, workspace_bytes - pos_bytes, st);
+    if (rc) return rc;
+    scatter_hits_kernel<<<(R + 255) / 256, 256, 0, st>>>(pos, sample_cnt, R, ray_index, n_rays);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_gather_hit_rays(const int* ray_index, int n_rays, int SR, const float* sample_loc, const int* sample_cnt,
+                                     const float* dirs, float* loc_out, int* cnt_out, float* dirs_out, void* stream) {
+    if (n_rays < 0 || SR <= 0) return PNERF_ERR_ARG;
+    if (n_rays == 0) return PNERF_OK;
+    if (!ray_index || !sample_loc || !sample_cnt || !loc_out || !cnt_out || (dirs && !dirs_out)) return PNERF_ERR_ARG;
+    const int64_t b = ((int64_t)n_rays * 32 + 255) / 256;
+    const int blocks = (int)(b > (int64_t)kSMs * 16 ? (int64_t)kSMs * 16 : b);
+    gather_hits_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ray_index, n_rays, SR, sample_loc, sample_cnt, dirs, loc_out, cnt_out, dirs_out);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
 
 extern "C" int64_t pnerf_scan_workspace_bytes(int64_t n) { return scan_workspace_bytes(n + 1) + align_up((n + 1) * 4, 256); }
 

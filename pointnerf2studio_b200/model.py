@@ -232,8 +232,9 @@ class NeuralPoints(nn.Module):
         t_mid = (end[:, :-1] + end[:, 1:]) / 2
         return t_mid[0].contiguous() if not jitter else t_mid.contiguous()
 
-    def query(self, ray_bundle, jitter=None, generator=None, want_stats=False, near=None, far=None):
-        """Rows G0/G2/Q on the cached grid.  Returns (QueryResult, origin, R_c2w)."""
+    def query(self, ray_bundle, jitter=None, generator=None, want_stats=False, near=None, far=None, compact=False):
+        """Rows G0/G2/Q on the cached grid.  Returns (QueryResult, origin, R_c2w, dirs); with compact=True the result and
+        `dirs` cover only the rays whose selection found an occupied position (QueryResult.ray_index)."""
         cfg = self.config
         if near is None:
             origin, R_c2w, near, far = self.camera_of(ray_bundle, with_near_far=True)
@@ -249,12 +250,13 @@ class NeuralPoints(nn.Module):
             self._last_jitter = (near, far, float(jitter), seed)
             q = native.sample_and_query(self.grid(), R, cfg.z_depth_dim, cfg.SR, cfg.K, int(self.kernel_size[0]),
                                         float(self.radius_limit_np), origin=origin, dirs=dirs, want_stats=want_stats,
-                                        jitter_gen=self._last_jitter)
-            return q, origin, R_c2w, dirs
+                                        jitter_gen=self._last_jitter, compact=compact)
+            return q, origin, R_c2w, (q.dirs if compact else dirs)
         t = self.coarse_t(R, near, far, jitter, generator)     # torch path: jitter 0 (shared table) or an explicit generator
         q = native.sample_and_query(self.grid(), R, cfg.z_depth_dim, cfg.SR, cfg.K, int(self.kernel_size[0]),
-                                    float(self.radius_limit_np), origin=origin, dirs=dirs, t_vals=t, want_stats=want_stats)
-        return q, origin, R_c2w, dirs
+                                    float(self.radius_limit_np), origin=origin, dirs=dirs, t_vals=t, want_stats=want_stats,
+                                    compact=compact)
+        return q, origin, R_c2w, (q.dirs if compact else dirs)
 
     def forward(self, ray_bundle):
         """Reference-shaped return value (SU:209): the 13 gathered tensors.  Compatibility API only --
@@ -374,7 +376,7 @@ class PointNerf(nn.Module):
     def _get_outputs(self, ray_bundle, generator=None):
         c = self.config
         npnts = self.neural_points
-        q, origin, R_c2w, dirs = npnts.query(ray_bundle, generator=generator)
+        q, origin, R_c2w, dirs = npnts.query(ray_bundle, generator=generator, compact=True)
         mode = native.make_mode(c.flow, training=self.training, bg=self._background_color.tolist(), vsize_z=c.vsize[2])
         cfg = {"mode": mode, "camera": native.make_camera(origin, R_c2w)}
         args = (cfg, q, dirs, npnts.points_xyz, npnts.points_Rw2c, npnts.points_embeding.view(-1, c.point_features_dim),
@@ -386,6 +388,10 @@ class PointNerf(nn.Module):
             rgb = native_tc.render_tc(*args, self.mlp_param_list())
         else:
             raise ValueError(c.precision)
+        # rays dropped by the hit-ray compaction keep the background colour (fill_invalid, SM:491-504)
+        R_total = q.R_total
+        bg = self._background_color.to(device=self._device, dtype=rgb.dtype)
+        rgb = bg.view(1, 3).expand(R_total, 3).index_copy(0, q.ray_index.long(), rgb)
         lib = native._lib.load()
         R, SR = q.sample_valid.shape
         ray_mask = torch.empty((R,), dtype=torch.int8, device=self._device)
@@ -396,12 +402,28 @@ class PointNerf(nn.Module):
         native.check(lib.pnerf_ray_compact(native._ptr(q.sample_valid), R, SR, native._ptr(ray_mask), native._ptr(ray_index),
                                            native._ptr(n_rays), native._ptr(ws), ws_bytes, native._stream()), "pnerf_ray_compact")
         native.LAUNCHES["n"] += 3
-        out = {"coarse_raycolor": rgb, "ray_mask": ray_mask}
+        full_mask = torch.zeros((R_total,), dtype=torch.int8, device=self._device).index_copy_(0, q.ray_index.long(), ray_mask)
+        out = {"coarse_raycolor": rgb, "ray_mask": full_mask}
         if self.training:
             out["conf_coefficient"] = ConfCoefficient(npnts.points_conf, q.sample_pidx, ray_mask, n_rays)
         self._last_query = q
         self._last_render = cfg.get("last")
         return out
+
+    def last_query_dense(self):
+        """The last call's query result over ALL its rays (tests / debugging): compacted rays scattered back."""
+        return self._last_query.dense()
+
+    def last_render_dense(self):
+        """Per-slot sigma (R,SR) / rgb (R,SR,3) of the last call over ALL its rays, zero for rays without samples."""
+        q, last = self._last_query, self._last_render
+        if q.ray_index is None:
+            return last
+        idx = q.ray_index.long()
+        SR = q.sample_valid.shape[1]
+        sig = torch.zeros((q.R_total, SR), dtype=torch.float32, device=idx.device).index_copy_(0, idx, last["sigma"])
+        rgb = torch.zeros((q.R_total, SR, 3), dtype=torch.float32, device=idx.device).index_copy_(0, idx, last["rgb"])
+        return {"sigma": sig, "rgb": rgb, "n_samples": last["n_samples"]}
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, ray_bundle, chunk=None):

@@ -126,6 +126,23 @@ class QueryResult:
     sample_pidx: torch.Tensor     # (R,SR,K) i32, -1 padded
     sample_valid: torch.Tensor    # (R,SR) u8
     stats: Optional[torch.Tensor] = None   # (2,) u64 as int64: voxel entries visited, candidates examined
+    # hit-ray compaction: when ray_index is set, the tensors above hold only the R' rays whose selection found an occupied
+    # position (row i = ray ray_index[i] of the R_total rays of the call), and `dirs` holds their directions
+    ray_index: Optional[torch.Tensor] = None
+    R_total: Optional[int] = None
+    dirs: Optional[torch.Tensor] = None
+
+    def dense(self) -> "QueryResult":
+        """The (R_total, ...) tensors of the uncompacted call (what the reference's mask_raypos stage produces)."""
+        if self.ray_index is None:
+            return self
+        R, (R2, SR, K) = self.R_total, self.sample_pidx.shape
+        dev, idx = self.sample_pidx.device, self.ray_index.long()
+        loc = torch.zeros((R, SR, 3), dtype=torch.float32, device=dev).index_copy_(0, idx, self.sample_loc)
+        cnt = torch.zeros((R,), dtype=torch.int32, device=dev).index_copy_(0, idx, self.sample_cnt)
+        pidx = torch.full((R, SR, K), -1, dtype=torch.int32, device=dev).index_copy_(0, idx, self.sample_pidx)
+        valid = torch.zeros((R, SR), dtype=torch.uint8, device=dev).index_copy_(0, idx, self.sample_valid)
+        return QueryResult(loc, cnt, pidx, valid, self.stats)
 
 
 def coarse_t(near: float, far: float, jitter: float, seed: int, R: int, D: int, device, want_u: bool = False):
@@ -140,17 +157,20 @@ def coarse_t(near: float, far: float, jitter: float, seed: int, R: int, D: int, 
 
 def sample_and_query(grid: VoxelGrid, R: int, D: int, SR: int, K: int, kernel_size0: int, radius: float,
                      raypos: Optional[torch.Tensor] = None, origin=None, dirs: Optional[torch.Tensor] = None,
-                     t_vals: Optional[torch.Tensor] = None, want_stats: bool = False, jitter_gen=None) -> QueryResult:
+                     t_vals: Optional[torch.Tensor] = None, want_stats: bool = False, jitter_gen=None,
+                     compact: bool = False) -> QueryResult:
     """Rows G0/G2/Q: select the first SR occupied coarse positions per ray and query K neighbours each.
     Position source: `raypos` (R,D,3), or origin + dirs * `t_vals` ((D,) or (R,D)), or -- `jitter_gen` =
-    (near, far, jitter, seed) -- jittered t generated inside the selection kernel."""
+    (near, far, jitter, seed) -- jittered t generated inside the selection kernel.
+    compact=True: the rays whose selection found nothing (5 of 6 for an object-centred view) are dropped right after the
+    selection -- the reference's own R -> R' step (CU:381-391) -- and the query and everything after it run on R' rays
+    (one host sync for R'); the result carries `ray_index`."""
     lib = _lib.load()
     dev = grid.cell_start.device
     loc = torch.empty((R, SR, 3), dtype=torch.float32, device=dev)
     cnt = torch.empty((R,), dtype=torch.int32, device=dev)
-    pidx = torch.empty((R, SR, K), dtype=torch.int32, device=dev)
-    valid = torch.empty((R, SR), dtype=torch.uint8, device=dev)
     stats = torch.zeros(2, dtype=torch.int64, device=dev) if want_stats else None
+    fill = 0 if compact else 1
     t_stride = 0
     if raypos is None and jitter_gen is None:
         assert dirs is not None and t_vals is not None and origin is not None
@@ -159,17 +179,35 @@ def sample_and_query(grid: VoxelGrid, R: int, D: int, SR: int, K: int, kernel_si
         if jitter_gen is not None:
             near, far, jitter, seed = jitter_gen
             check(lib.pnerf_sample_select_jitter(C.byref(grid.view), _f3(origin), _ptr(dirs, torch.float32), C.c_float(near),
-                                                 C.c_float(far), C.c_float(jitter), C.c_uint64(int(seed)), R, D, SR, _ptr(loc),
+                                                 C.c_float(far), C.c_float(jitter), C.c_uint64(int(seed)), R, D, SR, fill, _ptr(loc),
                                                  _ptr(cnt), _stream()), "pnerf_sample_select_jitter")
         else:
             check(lib.pnerf_sample_select(C.byref(grid.view), _ptr(raypos, torch.float32), _f3(origin) if origin is not None else None,
-                                          _ptr(dirs, torch.float32), _ptr(t_vals, torch.float32), t_stride, R, D, SR, _ptr(loc),
+                                          _ptr(dirs, torch.float32), _ptr(t_vals, torch.float32), t_stride, R, D, SR, fill, _ptr(loc),
                                           _ptr(cnt), _stream()), "pnerf_sample_select")
+    ray_index, R_total, dirs_c = None, None, None
+    if compact:
+        with Timers.span("compact"):
+            ray_index = torch.empty((max(R, 1),), dtype=torch.int32, device=dev)
+            n_dev = torch.empty((1,), dtype=torch.int32, device=dev)
+            ws_bytes = lib.pnerf_scan_workspace_bytes(R)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(lib.pnerf_hit_rays(_ptr(cnt), R, _ptr(ray_index), _ptr(n_dev), _ptr(ws), ws_bytes, _stream()), "pnerf_hit_rays")
+            R2 = int(n_dev.item()) if R > 0 else 0
+            loc2 = torch.empty((R2, SR, 3), dtype=torch.float32, device=dev)
+            cnt2 = torch.empty((R2,), dtype=torch.int32, device=dev)
+            dirs_c = torch.empty((R2, 3), dtype=torch.float32, device=dev) if dirs is not None else None
+            check(lib.pnerf_gather_hit_rays(_ptr(ray_index), R2, SR, _ptr(loc), _ptr(cnt), _ptr(dirs, torch.float32), _ptr(loc2), _ptr(cnt2),
+                                            _ptr(dirs_c), _stream()), "pnerf_gather_hit_rays")
+        LAUNCHES["n"] += 5
+        ray_index, R_total, loc, cnt, R = ray_index[:R2], R, loc2, cnt2, R2
+    pidx = torch.empty((R, SR, K), dtype=torch.int32, device=dev)
+    valid = torch.empty((R, SR), dtype=torch.uint8, device=dev)
     with Timers.span("query"):
         check(lib.pnerf_query(C.byref(grid.view), _ptr(loc), _ptr(cnt), R, SR, K, int(kernel_size0), C.c_float(float(radius)),
                               _ptr(pidx), _ptr(valid), _ptr(stats), _stream()), "pnerf_query")
     LAUNCHES["n"] += 2
-    return QueryResult(loc, cnt, pidx, valid, stats)
+    return QueryResult(loc, cnt, pidx, valid, stats, ray_index, R_total, dirs_c)
 
 
 def compact_rays(q: QueryResult):

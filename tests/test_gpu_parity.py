@@ -186,7 +186,7 @@ def test_field_composite_fp32_forward_backward(flow):
     out = model.get_outputs(_bundle(cam, pix))
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out["ray_mask"].cpu().numpy(), cm)
-    q = model._last_query
+    q = model.last_query_dense()
     np.testing.assert_array_equal(q.sample_pidx.cpu().numpy(), pidx_o)
     # per-sample sigma / rgb
     keep = cm.astype(bool)
@@ -233,7 +233,7 @@ def test_golden_reference_fixture_fp32():
     out = model.get_outputs(_bundle(cam, pix))
     np.testing.assert_array_equal(out["ray_mask"].cpu().numpy(), G["ray_mask"])
     keep = G["ray_mask"].astype(bool)
-    q = model._last_query
+    q = model.last_query_dense()
     np.testing.assert_array_equal(q.sample_pidx.cpu().numpy()[keep], G["pidx"].astype(np.int32))
     np.testing.assert_array_equal(q.sample_loc.cpu().numpy()[keep], G["loc_w"])
     C = out["coarse_raycolor"].detach().cpu().numpy()

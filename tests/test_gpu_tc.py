@@ -33,12 +33,12 @@ def test_tc_forward_matches_fp32_oracle(name, flow):
     model.eval()
     with torch.no_grad():
         out = model.get_outputs(_bundle(cam, pix))
-    np.testing.assert_array_equal(model._last_query.sample_pidx.cpu().numpy(), pidx)      # same neighbours first
+    np.testing.assert_array_equal(model.last_query_dense().sample_pidx.cpu().numpy(), pidx)      # same neighbours first
     np.testing.assert_array_equal(out["ray_mask"].cpu().numpy(), cm)
     got = out["coarse_raycolor"].cpu().numpy()
     want = ref["coarse_raycolor"].detach().numpy()
     keep = cm.astype(bool)
-    last = model._last_render
+    last = model.last_render_dense()
     sig = last["sigma"].cpu().numpy()[keep]
     rgb = last["rgb"].cpu().numpy()[keep]
     dec = ref["decoded"].detach().numpy().reshape(-1, s["SR"], 4)
