@@ -297,8 +297,10 @@ def main():
         R = TRAIN_RAYS
         gt_host = torch.rand((R, 3), generator=torch.Generator().manual_seed(9)).pin_memory()
         gt_dev = gt_host.cuda()
+        from pointnerf2studio_b200.optim import make_optimizers
         from pointnerf2studio_b200.parallel import allreduce_gradients
         params = [p for p in model.parameters() if p.requires_grad]
+        opts, scheds = make_optimizers(model)       # the plugin's two Adam groups + exponential decay (studio_config.py:33-48)
 
         def train_step(rb, gt):
             for p in params:
@@ -309,6 +311,9 @@ def main():
             loss.backward()
             if dist is not None:
                 allreduce_gradients(params, dist)
+            for k in opts:
+                opts[k].step()
+                scheds[k].step()
             return loss
 
         def step_dev():
@@ -322,7 +327,8 @@ def main():
         h2d = sum(t.numel() * t.element_size() for t in host) + gt_host.numel() * 4
         d2h = 4
         metric = "train rays/s"
-        workload = "training step fwd+bwd, 4096 rays per rank, 1M-point synthetic cloud, K=8, SR=80 (configs[2])"
+        workload = ("training step fwd+bwd+Adam (fields 5e-4, neural points 2e-3), 4096 rays per rank, 1M-point synthetic cloud, "
+                    "K=8, SR=80 (configs[2])")
 
     # ---- warm-up (also builds the cached voxel grid) + occupancy statistics of this view (not timed)
     for _ in range(max(args.warmup, 1)):

@@ -241,6 +241,15 @@ int pnerf_conf_loss(const float* conf, const int* sample_pidx, const int8_t* ray
  * A: bf16 row major; Wp: bf16 in the K-slab layout [K/8][N][8] (see csrc/umma.cuh). */
 int pnerf_umma_selftest(const void* A, const void* Wp, float* D, int N, int K, void* stream);
 
+/* ---------------------------------------------------------------- optimiser step
+ * torch.optim.Adam (betas, eps, bias correction; no weight decay, no amsgrad -- what nerfstudio's AdamOptimizerConfig builds for
+ * the plugin's two groups, studio_config.py:33-48) for up to PNERF_ADAM_MAX_SEGS tensors in ONE launch: p, m, v updated in place
+ * from g * grad_scale.  `step` is the tensor's own 1-based step count (torch keeps it per parameter: a parameter without a gradient
+ * is skipped and does not advance); lr is per tensor (the host applies the schedule). */
+#define PNERF_ADAM_MAX_SEGS 32
+typedef struct { float* p; const float* g; float* m; float* v; int64_t n; int64_t step; float lr; } pnerf_adam_seg;
+int pnerf_adam_step(const pnerf_adam_seg* segs_h, int n_segs, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
 /* Micro-benchmarks of the resources the tensor-core kernels lean on (one CTA per SM, all SMs): which = 0 tcgen05.mma
  * rate (param = N), 1 L2 -> shared bulk-copy ring (param = chunk bytes, src >= 557056 bytes), 2 tcgen05.ld rate
  * (param = warps).  out[148] = cycles for `iters` operations per CTA. */
