@@ -230,6 +230,14 @@ int pnerf_composite_backward(const pnerf_camera* cam_h, const pnerf_mode* mode_h
                              const uint8_t* sample_valid, const float* sigma, const float* rgb,
                              const float* d_out, int R, int SR, float* d_sigma, float* d_rgb, void* stream);
 
+/* Hole probing of the original flow (models/neural_points_volumetric_model.py:331-362): per ray the sample of
+ * largest opacity (first on ties), its world position, the distance to its nearest gathered neighbour (invalid slots gather point 0)
+ * and the (weight * confidence)-averaged colour / dir / conf / embedding of its K neighbours.  Outputs by ray: (R), (R,3), (R),
+ * (R,3), (R,3), (R), (R,32).  sigma as produced by the field kernels (by slot). */
+int pnerf_probe(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mode* mode_h, const float* sample_loc,
+                const uint8_t* sample_valid, const float* sigma, const int* sample_pidx, int R, int SR, int K, float* max_opacity,
+                float* max_loc, float* far_dist, float* avg_color, float* avg_dir, float* avg_conf, float* avg_embed, void* stream);
+
 /* Confidence ("zero-one") loss term of SM:288-292,427-429 over ALL R''*SR*K slots (invalid slots
  * read point 0, SU:194): adds the value to loss_out[0] and its gradient to g_conf (N). */
 int pnerf_conf_loss(const float* conf, const int* sample_pidx, const int8_t* ray_mask, int R, int SR, int K,

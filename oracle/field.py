@@ -288,6 +288,24 @@ def render(points, W: FieldWeights, origin, dirs, R_c2w, pidx, loc_w, ray_mask, 
     delta = ray_dist(g["loc_pers"], valid, vsize_z)
     C, bw, opacity, T_end = composite(dec, valid, delta, mode=mode, bg=bg, training=training)
     out = {"coarse_raycolor": fill_invalid(C, ray_mask, bg), "ray_mask": torch.as_tensor(ray_mask),
-           "decoded": dec, "valid": valid, "delta": delta, "blend_weight": bw, "C_valid": C,
+           "decoded": dec, "valid": valid, "delta": delta, "blend_weight": bw, "C_valid": C, "opacity": opacity, "gather": g,
            "conf_coefficient": ex["conf_coefficient"], "extras": ex}
     return out
+
+
+# ----------------------------------------------------------------------------- hole probing
+def probe(points, g, extras, opacity, valid_rays=None):
+    """models/neural_points_volumetric_model.py:331-362 restated.  g = gather(...) of the surviving rays, extras = the third
+    return value of field_forward, opacity (R2,SR) = per-sample opacity of composite().  Returns the probe outputs by ray."""
+    R2, SR, K = g["mask"].shape
+    mx, ind = torch.max(opacity, dim=-1, keepdim=True)                        # NPV:335
+    take = lambda t: torch.gather(t, 1, ind.view(R2, 1, *([1] * (t.dim() - 2))).expand(-1, 1, *t.shape[2:])).squeeze(1)
+    loc = take(g["loc_w"])                                                   # (R2,3)
+    w = take(extras["weight_used"] * extras["conf_coefficient"])[..., None]  # NPV:340 (R2,K,1)
+    xyz = take(g["xyz"])                                                     # (R2,K,3) incl. point 0 at invalid slots
+    far = torch.norm(xyz - loc[:, None, :], dim=-1).min(-1, keepdim=True)[0]  # NPV:344
+    out = {"ray_max_shading_opacity": mx, "ray_max_sample_loc_w": loc, "ray_max_far_dist": far,
+           "shading_avg_color": (take(g["color"]) * w).sum(-2), "shading_avg_dir": (take(g["dir"]) * w).sum(-2),
+           "shading_avg_conf": (take(g["conf"]) * w).sum(-2), "shading_avg_embedding": (take(g["embed"]) * w).sum(-2)}
+    return out
+

@@ -190,6 +190,73 @@ __global__ void __launch_bounds__(256) conf_loss_kernel(const float* __restrict_
     if ((threadIdx.x & 31) == 0 && part != 0.f && loss_out) atomicAdd(loss_out, part * weight * inv_n);
 }
 
+// Hole probing (original flow, neural_points_volumetric_model.py:331-362): per ray the sample of largest opacity, its position, the
+// distance to its nearest gathered neighbour and the (weight * confidence)-averaged attributes of its K neighbours -- the candidates
+// run/train_studio.py:335-444 turns into new neural points.  One warp per ray; lanes k < K own the neighbours of the chosen sample.
+struct ProbeOut { float *opacity, *loc, *far_dist, *color, *dir, *conf, *embed; };
+__global__ void __launch_bounds__(256) probe_kernel(CompCam cam, pnerf_mode mode, const float* __restrict__ sample_loc,
+                                                     const uint8_t* __restrict__ sample_valid, const float* __restrict__ sigma,
+                                                     const int* __restrict__ sample_pidx, const float* __restrict__ xyz,
+                                                     const float* __restrict__ embed, const float* __restrict__ color,
+                                                     const float* __restrict__ dir, const float* __restrict__ conf, int R, int SR, int K,
+                                                     ProbeOut o) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
+        const int64_t base = (int64_t)r * SR;
+        RayState st;
+        ray_forward(cam, mode.vsize_z, sample_loc + 3 * base, sample_valid + base, sigma + base, SR, lane, st);
+        // torch.max over the SR slots: largest opacity, first index on ties
+        float best = -1.f; int bi = 0;
+#pragma unroll
+        for (int c = 0; c < MAXC; c++) {
+            const int s = c * 32 + lane;
+            if (s < SR && st.alpha[c] > best) { best = st.alpha[c]; bi = s; }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        const float* q = sample_loc + 3 * (base + bi);
+        const float qx = q[0], qy = q[1], qz = q[2];
+        int p = -1; float dist = INFINITY, wraw = 0.f, cc = 1.f;
+        if (lane < K) {
+            p = sample_pidx[(base + bi) * K + lane];
+            const int idx = max(p, 0);                                  // invalid slots gather point 0 (SU:194)
+            const float dx = xyz[3 * (int64_t)idx] - qx, dy = xyz[3 * (int64_t)idx + 1] - qy, dz = xyz[3 * (int64_t)idx + 2] - qz;
+            dist = sqrtf(dx * dx + dy * dy + dz * dz);
+            wraw = p >= 0 ? 1.f / fmaxf(dist, 1e-6f) : 0.f;
+            cc = fminf(fmaxf(conf[idx], 1e-4f), 1.f);
+        }
+        float wsum = wraw, dmin = dist;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            wsum += __shfl_xor_sync(0xffffffffu, wsum, off);
+            dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, off));
+        }
+        float w = wraw / fmaxf(wsum, 1e-8f);
+        if (mode.weight_conf) w *= cc;                                   // the aggregator's returned weight (PA:826)
+        const float sw = w * cc;                                         // NPV:340: weight * conf_coefficient
+        // averages: lane j < 32 owns embedding dim j; lanes 0..2 colour, 3..5 dir, 6 conf (second pass)
+        float e_acc = 0.f, a_acc = 0.f;
+        for (int k = 0; k < K; k++) {
+            const float swk = __shfl_sync(0xffffffffu, sw, k);
+            const int idx = max(__shfl_sync(0xffffffffu, p, k), 0);
+            e_acc = fmaf(swk, embed[(int64_t)idx * 32 + lane], e_acc);
+            if (lane < 3) a_acc = fmaf(swk, color[3 * (int64_t)idx + lane], a_acc);
+            else if (lane < 6) a_acc = fmaf(swk, dir[3 * (int64_t)idx + lane - 3], a_acc);
+            else if (lane == 6) a_acc = fmaf(swk, conf[idx], a_acc);                       // the raw gathered confidence (NPV:350,355)
+        }
+        o.embed[(int64_t)r * 32 + lane] = e_acc;
+        if (lane < 3) { o.color[3 * (int64_t)r + lane] = a_acc; o.loc[3 * (int64_t)r + lane] = lane == 0 ? qx : (lane == 1 ? qy : qz); }
+        else if (lane < 6) o.dir[3 * (int64_t)r + lane - 3] = a_acc;
+        else if (lane == 6) o.conf[r] = a_acc;
+        else if (lane == 7) { o.opacity[r] = best; o.far_dist[r] = dmin; }
+    }
+}
+
 CompCam make_ccam(const pnerf_camera* c) {
     CompCam k;
     for (int i = 0; i < 3; i++) { k.o[i] = c->origin[i]; k.Rz[i] = c->R_c2w[3 * i + 2]; }
@@ -225,6 +292,22 @@ extern "C" int pnerf_composite_backward(const pnerf_camera* cam, const pnerf_mod
     if (!sample_loc || !sample_valid || !sigma || !rgb || !d_out || !d_sigma || !d_rgb) return PNERF_ERR_ARG;
     composite_bwd_kernel<<<ray_blocks(R), 256, 0, (cudaStream_t)stream>>>(make_ccam(cam), *mode, sample_loc, sample_valid, sigma,
                                                                          rgb, d_out, R, SR, d_sigma, d_rgb);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_probe(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mode* mode, const float* sample_loc,
+                           const uint8_t* sample_valid, const float* sigma, const int* sample_pidx, int R, int SR, int K,
+                           float* max_opacity, float* max_loc, float* far_dist, float* avg_color, float* avg_dir, float* avg_conf,
+                           float* avg_embed, void* stream) {
+    if (!pts || !cam || !mode || R < 0 || SR <= 0 || SR > 32 * MAXC || K <= 0 || K > 32) return PNERF_ERR_ARG;
+    if (R == 0) return PNERF_OK;
+    if (!sample_loc || !sample_valid || !sigma || !sample_pidx || !max_opacity || !max_loc || !far_dist || !avg_color || !avg_dir ||
+        !avg_conf || !avg_embed)
+        return PNERF_ERR_ARG;
+    ProbeOut o = {max_opacity, max_loc, far_dist, avg_color, avg_dir, avg_conf, avg_embed};
+    probe_kernel<<<ray_blocks(R), 256, 0, (cudaStream_t)stream>>>(make_ccam(cam), *mode, sample_loc, sample_valid, sigma, sample_pidx,
+                                                                 pts->xyz, pts->embed, pts->color, pts->dir, pts->conf, R, SR, K, o);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }

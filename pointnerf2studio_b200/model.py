@@ -196,6 +196,36 @@ class NeuralPoints(nn.Module):
             self._grid_key = key
         return self._grid
 
+    # ---- point-cloud surgery of the original flow (models/neural_points/neural_points.py:341-393); both replace the parameter
+    # tensors, so the cached voxel grid is rebuilt on the next query and optimiser state must be re-created by the caller
+    # (run/train_studio.py:677-683 does clean_optimizer / setup_optimizer around them)
+    def _replace(self, xyz, embed, conf, dirn, color):
+        c = self.config
+        self.points_xyz = Parameter(xyz.contiguous(), requires_grad=False)
+        self.points_embeding = Parameter(embed.contiguous(), requires_grad=c.feat_grad)
+        self.points_conf = Parameter(conf.contiguous(), requires_grad=c.conf_grad)
+        self.points_dir = Parameter(dirn.contiguous(), requires_grad=c.dir_grad)
+        self.points_color = Parameter(color.contiguous(), requires_grad=c.color_grad)
+        self._grid, self._grid_key = None, None
+
+    @torch.no_grad()
+    def prune(self, thresh: float) -> int:
+        """NP:341-362: keep the points whose confidence is >= thresh.  Returns the number of pruned points."""
+        mask = self.points_conf[0, :, 0] >= thresh
+        n_pruned = int((~mask).sum())
+        self._replace(self.points_xyz[mask], self.points_embeding[:, mask], self.points_conf[:, mask], self.points_dir[:, mask],
+                      self.points_color[:, mask])
+        return n_pruned
+
+    @torch.no_grad()
+    def grow_points(self, add_xyz, add_embedding, add_color, add_dir, add_conf) -> int:
+        """NP:367-393: append points (N_add,3), (N_add,32), (N_add,3), (N_add,3), (N_add,1)."""
+        dev = self.points_xyz.device
+        cat = lambda a, b: torch.cat([a, b.to(dev).float()[None]], dim=1)
+        self._replace(torch.cat([self.points_xyz, add_xyz.to(dev).float()], dim=0), cat(self.points_embeding, add_embedding),
+                      cat(self.points_conf, add_conf), cat(self.points_dir, add_dir), cat(self.points_color, add_color))
+        return int(add_xyz.shape[0])
+
     def get_hyperparameters(self, vsize_np, point_xyz_w_tensor, ranges=None):
         """SU:115-127, same return triple."""
         f = native.get_hyperparameters(point_xyz_w_tensor, vsize_np, self.config.vscale, self.config.kernel_size, ranges)
@@ -424,6 +454,44 @@ class PointNerf(nn.Module):
         sig = torch.zeros((q.R_total, SR), dtype=torch.float32, device=idx.device).index_copy_(0, idx, last["sigma"])
         rgb = torch.zeros((q.R_total, SR, 3), dtype=torch.float32, device=idx.device).index_copy_(0, idx, last["rgb"])
         return {"sigma": sig, "rgb": rgb, "n_samples": last["n_samples"]}
+
+    @torch.no_grad()
+    def probe(self, ray_bundle):
+        """Hole probing of the original flow (models/neural_points_volumetric_model.py:331-362, consumed by probe_hole,
+        run/train_studio.py:335-444): renders the rays and returns, besides `coarse_raycolor` / `ray_mask`, per ray the largest
+        sample opacity, that sample's position, its distance to the nearest neighbour and the (weight x confidence)-averaged
+        attributes of its neighbours -- all (R, .) tensors, zero for rays without neighbours."""
+        import ctypes as C
+        was_training = self.training
+        self.eval()
+        try:
+            out = self.get_outputs(ray_bundle)
+        finally:
+            self.train(was_training)
+        q, last, npnts, c = self._last_query, self._last_render, self.neural_points, self.config
+        R2, SR, K = q.sample_pidx.shape
+        dev = self._device
+        lib = native._lib.load()
+        origin, R_c2w = npnts.camera_of(ray_bundle)
+        mode = native.make_mode(c.flow, training=False, bg=self._background_color.tolist(), vsize_z=c.vsize[2])
+        cam = native.make_camera(origin, R_c2w)
+        pts = native.make_points(npnts.points_xyz.detach(), npnts.points_embeding.detach().view(-1, c.point_features_dim),
+                                 npnts.points_color.detach().view(-1, 3), npnts.points_dir.detach().view(-1, 3),
+                                 npnts.points_conf.detach().view(-1, 1), npnts.points_Rw2c)
+        shapes = {"ray_max_shading_opacity": 1, "ray_max_sample_loc_w": 3, "ray_max_far_dist": 1, "shading_avg_color": 3,
+                  "shading_avg_dir": 3, "shading_avg_conf": 1, "shading_avg_embedding": c.point_features_dim}
+        t = {k: torch.zeros((R2, n), dtype=torch.float32, device=dev) for k, n in shapes.items()}
+        native.check(lib.pnerf_probe(C.byref(pts), C.byref(cam), C.byref(mode), native._ptr(q.sample_loc), native._ptr(q.sample_valid),
+                                     native._ptr(last["sigma"]), native._ptr(q.sample_pidx), R2, SR, K,
+                                     native._ptr(t["ray_max_shading_opacity"]), native._ptr(t["ray_max_sample_loc_w"]),
+                                     native._ptr(t["ray_max_far_dist"]), native._ptr(t["shading_avg_color"]),
+                                     native._ptr(t["shading_avg_dir"]), native._ptr(t["shading_avg_conf"]),
+                                     native._ptr(t["shading_avg_embedding"]), native._stream()), "pnerf_probe")
+        idx = q.ray_index.long()
+        keep = out["ray_mask"].to(torch.float32)[:, None]
+        for k, n in shapes.items():
+            out[k] = torch.zeros((q.R_total, n), dtype=torch.float32, device=dev).index_copy_(0, idx, t[k]) * keep
+        return out
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, ray_bundle, chunk=None):

@@ -49,11 +49,11 @@ def _bundle(cam, pix):
                      metadata={"camrotc2w": _cuda(cam.R_c2w)})
 
 
-def _oracle_query(cloud_xyz, cam, pix, SR, K, P, ks, D=400, jitter=0.0):
-    frame = gq.hyperparameters(cloud_xyz, [0.004] * 3, [2, 2, 2], list(ks), RANGES)
+def _oracle_query(cloud_xyz, cam, pix, SR, K, P, ks, D=400, jitter=0.0, vsize=0.004):
+    frame = gq.hyperparameters(cloud_xyz, [vsize] * 3, [2, 2, 2], list(ks), RANGES)
     raypos, t_mid = of.coarse_positions(torch.from_numpy(cam.origin), torch.from_numpy(cam.rays(pix)), D, cam.near, cam.far,
                                         jitter=jitter, generator=torch.Generator().manual_seed(3))
-    radius = np.float32(0.016)
+    radius = np.float32(4 * vsize)                       # SU:110
     pidx, loc, mask, hit, stats = query_c.woord_query_grid_point_index(raypos.numpy(), cloud_xyz, list(ks), [3, 3, 3], SR, K,
                                                                      frame, P, radius, want_stats=True)
     return frame, raypos, t_mid, pidx, loc, mask, hit, stats
@@ -63,13 +63,16 @@ SCENES = {
     "config1": dict(n=50000, radii=(0.11, 0.16, 0.2), SR=40, K=8, P=12, ks=(3, 3, 3), rays=1024),
     "k16_5cube": dict(n=20000, radii=(0.07, 0.1), SR=24, K=16, P=10, ks=(5, 5, 5), rays=600),
     "tinyP": dict(n=20000, radii=(0.05, 0.07), SR=16, K=4, P=3, ks=(3, 3, 3), rays=512),
+    # BASELINE configs[3] geometry (dev_scripts/w_scannet_etf/scene101_points.sh:24-37): vsize 0.008 x vscale 2, radius 0.032, P = 30, SR = 24
+    "scannet_like": dict(n=60000, radii=(0.14, 0.2), SR=24, K=8, P=30, ks=(3, 3, 3), rays=700, vsize=0.008),
 }
 
 
 def _scene(name):
     from pointnerf2studio_b200.synth import make_camera, make_cloud
     s = SCENES[name]
-    cloud = make_cloud(s["n"], seed=1234 + len(name), radii=s["radii"], P=s["P"])
+    cloud = make_cloud(s["n"], seed=1234 + len(name), radii=s["radii"], P=s["P"], scaled_vsize=2 * s.get("vsize", 0.004),
+                       kernel_size=s["ks"])
     cam = make_camera()
     rng = np.random.default_rng(5)
     c = cam.H // 2
@@ -83,9 +86,11 @@ def _scene(name):
 def test_grid_select_query_bit_exact(name):
     from pointnerf2studio_b200 import native
     s, cloud, cam, pix = _scene(name)
-    frame_o, raypos, t_mid, pidx_o, loc_o, mask_o, hit_o, stats_o = _oracle_query(cloud.xyz, cam, pix, s["SR"], s["K"], s["P"], s["ks"])
+    vs = s.get("vsize", 0.004)
+    frame_o, raypos, t_mid, pidx_o, loc_o, mask_o, hit_o, stats_o = _oracle_query(cloud.xyz, cam, pix, s["SR"], s["K"], s["P"], s["ks"],
+                                                                                 vsize=vs)
     xyz = _cuda(cloud.xyz)
-    frame = native.get_hyperparameters(xyz, [0.004] * 3, [2, 2, 2], list(s["ks"]), RANGES)
+    frame = native.get_hyperparameters(xyz, [vs] * 3, [2, 2, 2], list(s["ks"]), RANGES)
     np.testing.assert_array_equal(frame.lo, frame_o.lo)
     np.testing.assert_array_equal(frame.dim, frame_o.dim)
     grid = native.VoxelGrid(xyz, frame, s["P"], [3, 3, 3])
@@ -106,10 +111,11 @@ def test_grid_select_query_bit_exact(name):
     R = len(pix)
     for src in ("raypos", "t_shared"):
         if src == "raypos":
-            q = native.sample_and_query(grid, R, 400, s["SR"], s["K"], s["ks"][0], 0.016, raypos=_cuda(raypos.numpy()), want_stats=True)
+            q = native.sample_and_query(grid, R, 400, s["SR"], s["K"], s["ks"][0], float(np.float32(4 * vs)), raypos=_cuda(raypos.numpy()),
+                                        want_stats=True)
         else:
-            q = native.sample_and_query(grid, R, 400, s["SR"], s["K"], s["ks"][0], 0.016, origin=cam.origin, dirs=_cuda(cam.rays(pix)),
-                                        t_vals=_cuda(t_mid[0].numpy()), want_stats=True)
+            q = native.sample_and_query(grid, R, 400, s["SR"], s["K"], s["ks"][0], float(np.float32(4 * vs)), origin=cam.origin,
+                                        dirs=_cuda(cam.rays(pix)), t_vals=_cuda(t_mid[0].numpy()), want_stats=True)
         torch.cuda.synchronize()
         np.testing.assert_array_equal(q.sample_loc.cpu().numpy(), loc_o)
         np.testing.assert_array_equal(q.sample_cnt.cpu().numpy(), mask_o.sum(1))
@@ -160,7 +166,7 @@ def test_edge_cases_empty_and_all_miss():
 
 
 # ------------------------------------------------------------------------------------------------ field + compositing
-def _oracle_render(cloud, cam, pix, W, pidx, loc, hit, SR, mode, training=True, bf16=False):
+def _oracle_render(cloud, cam, pix, W, pidx, loc, hit, SR, mode, training=True, bf16=False, vsize_z=0.004):
     cp, cl, cm = gq.compact_rays(pidx, loc, hit)
     pts = {"xyz": torch.from_numpy(cloud.xyz), "Rw2c": torch.from_numpy(cloud.Rw2c)}
     for k in ("embed", "color", "dir", "conf"):
@@ -169,7 +175,7 @@ def _oracle_render(cloud, cam, pix, W, pidx, loc, hit, SR, mode, training=True, 
         v.requires_grad_(True)
         v.grad = None
     out = of.render(pts, W, torch.from_numpy(cam.origin), torch.from_numpy(cam.rays(pix)), torch.from_numpy(cam.R_c2w), cp, cl, cm,
-                    0.004, SR, mode=mode, training=training, bf16=bf16)
+                    vsize_z, SR, mode=mode, training=training, bf16=bf16)
     return out, pts, cm
 
 
@@ -309,3 +315,44 @@ def test_in_kernel_jitter_replays_through_t_table():
     np.testing.assert_array_equal(qa.sample_loc.cpu().numpy(), loc_o)
     np.testing.assert_array_equal(qa.sample_pidx.cpu().numpy(), pidx_o)
     assert int(qa.sample_cnt.sum()) > 1000
+
+
+@pytest.mark.parametrize("flow", ["original", "plugin"])
+def test_probe_prune_grow(flow):
+    """the hole-probing outputs (NPV:331-362) against the oracle restatement on the fp32 path, then pruning
+    by confidence and growing with the probed candidates (NP:341-393): the voxel grid is rebuilt and the grown cloud renders."""
+    s, cloud, cam, pix = _scene("config1")
+    pix = pix[:384]
+    SR = 24
+    W = of.FieldWeights.random(seed=7, scale=1.6)
+    _, _, _, pidx_o, loc_o, mask_o, hit_o, _ = _oracle_query(cloud.xyz, cam, pix, SR, 8, 12, (3, 3, 3))
+    with torch.no_grad():
+        out_o, pts_o, cm = _oracle_render(cloud, cam, pix, W, pidx_o, loc_o, hit_o, SR, flow, training=False)
+        ref = of.probe(pts_o, out_o["gather"], out_o["extras"], out_o["opacity"])
+    model = _make_model(cloud, "fp32", flow, SR=SR, weights=W)
+    got = model.probe(_bundle(cam, pix))
+    keep = cm.astype(bool)
+    np.testing.assert_array_equal(got["ray_mask"].cpu().numpy(), cm)
+    for k, v in ref.items():
+        g = got[k].cpu().numpy()
+        np.testing.assert_allclose(g[keep], v.numpy(), rtol=2e-4, atol=2e-5, err_msg=k)
+        assert np.all(g[~keep] == 0), k
+    # prune + grow
+    npnts = model.neural_points
+    n0 = npnts.points_xyz.shape[0]
+    thr = 0.3
+    expect = int((torch.from_numpy(cloud.conf)[:, 0] < thr).sum())
+    assert npnts.prune(thr) == expect and npnts.points_xyz.shape[0] == n0 - expect
+    assert npnts.points_embeding.shape == (1, n0 - expect, 32) and float(npnts.points_conf.detach().min()) >= thr
+    cand = (got["ray_max_shading_opacity"][:, 0] > 0.3) & (got["ray_mask"] > 0)
+    n_add = npnts.grow_points(got["ray_max_sample_loc_w"][cand], got["shading_avg_embedding"][cand], got["shading_avg_color"][cand],
+                              got["shading_avg_dir"][cand], got["shading_avg_conf"][cand] * 0.4)
+    assert n_add == int(cand.sum()) and npnts.points_xyz.shape[0] == n0 - expect + n_add
+    model.eval()
+    with torch.no_grad():
+        out = model.get_outputs(_bundle(cam, pix))
+    assert npnts.grid().n == n0 - expect + n_add and bool(torch.isfinite(out["coarse_raycolor"]).all())
+    # the grown cloud's query still matches the oracle querier run on the new cloud
+    xyz_new = npnts.points_xyz.detach().cpu().numpy()
+    _, _, _, pidx_n, loc_n, mask_n, hit_n, _ = _oracle_query(xyz_new, cam, pix, SR, 8, 12, (3, 3, 3))
+    np.testing.assert_array_equal(model.last_query_dense().sample_pidx.cpu().numpy(), pidx_n)

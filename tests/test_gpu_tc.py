@@ -23,13 +23,15 @@ def _weights(flow):
     return of.FieldWeights.from_aggregator(sd, prefix="")
 
 
-@pytest.mark.parametrize("name,flow", [("config1", "plugin"), ("config1", "original"), ("k16_5cube", "plugin"), ("tinyP", "plugin")])
+@pytest.mark.parametrize("name,flow", [("config1", "plugin"), ("config1", "original"), ("k16_5cube", "plugin"), ("tinyP", "plugin"),
+                                       ("scannet_like", "plugin")])
 def test_tc_forward_matches_fp32_oracle(name, flow):
     s, cloud, cam, pix = _scene(name)
+    vs = s.get("vsize", 0.004)
     W = _weights(flow) if flow == "original" else of.FieldWeights.random(seed=3, scale=1.5)
-    frame, raypos, t_mid, pidx, loc, mask, hit, _ = _oracle_query(cloud.xyz, cam, pix, s["SR"], s["K"], s["P"], s["ks"])
-    ref, _, cm = _oracle_render(cloud, cam, pix, W, pidx, loc, hit, s["SR"], flow, training=False)
-    model = _make_model(cloud, "bf16", flow, SR=s["SR"], K=s["K"], P=s["P"], ks=s["ks"], weights=W)
+    frame, raypos, t_mid, pidx, loc, mask, hit, _ = _oracle_query(cloud.xyz, cam, pix, s["SR"], s["K"], s["P"], s["ks"], vsize=vs)
+    ref, _, cm = _oracle_render(cloud, cam, pix, W, pidx, loc, hit, s["SR"], flow, training=False, vsize_z=vs)
+    model = _make_model(cloud, "bf16", flow, SR=s["SR"], K=s["K"], P=s["P"], ks=s["ks"], weights=W, vsize=[vs] * 3)
     model.eval()
     with torch.no_grad():
         out = model.get_outputs(_bundle(cam, pix))
