@@ -617,149 +617,190 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
 
 // ---------------------------------------------------------------------------------------------- colour network
 // mlp_color 280 -> 128 -> 128 -> 128 (LeakyReLU) + rgb head 128 -> 3 (sigmoid, *1.002 - 0.001), SM:355-359.
-// One CTA = 128 threads = 128 samples per tile; all three weight matrices stay resident in shared memory
-// (139 KB), the A operand is [F_s 256 | PE(v) 24 | 0 x 8] built from the bf16 features of field_tc_kernel.
+// CTA pairs again (cta_group::2, M = 256 = 128 samples per CTA, N = 128): each CTA keeps only ITS 64 output features of the three
+// weight matrices resident (68 KB instead of 136 KB), which leaves room for TWO sample-tile slots per CTA.  Warps 0-3 / 4-7 own
+// slot 0 / 1 (thread = sample = TMEM lane): gather the bf16 features of field_tc_kernel into the A operand [F_s 256 | PE(v) 24 | 0 x 8],
+// then the three epilogues; warp 8 of the leader issues the MMAs for whichever slot is ready (the weights are resident, so the order
+// is free): one slot's gather and epilogues hide under the other's MMAs.  v1 (one slot, 128 threads, everything serial per tile) ran
+// at 12.6 % tensor-pipe activity, 18 k clk per tile.
 struct ColorParams {
     const __nv_bfloat16* F;
     const int* sample_ids;
     const float* dirs;
-    const uint8_t* wpack_c;        // Wc1 | Wc2 | Wc3, K-slab packed
+    const uint8_t* wpack_c;        // Wc1 | Wc2 | Wc3, each as two N-halves of k-slabs [k/8][64][8]
     const float *bc1, *bc2, *bc3, *wc4, *bc4;
     Cam cam;
     int S, SR, n_tiles;
     float slope;
     float* rgb;                    // (R*SR,3) by slot
-    __nv_bfloat16* C3;             // optional (S,128) dump of the last hidden layer (training)
 };
 
+constexpr int C1H_BYTES = C1_BYTES / 2, C2H_BYTES = C2_BYTES / 2;
 struct SmemC {
-    uint8_t A[A_BYTES];
-    uint8_t W1[C1_BYTES];
-    uint8_t W2[C2_BYTES];
-    uint8_t W3[C2_BYTES];
+    uint8_t A[2][A_BYTES];
+    uint8_t W1[C1H_BYTES];
+    uint8_t W2[C2H_BYTES];
+    uint8_t W3[C2H_BYTES];
     float bias[3][HC];
     float w4[3][HC];
-    uint64_t bar_w, bar_mma;
+    uint64_t bar_w, a_ready[2], acc_full[2];
     uint32_t tmem_base;
 };
+static_assert(sizeof(SmemC) <= 232448, "color_tc_kernel shared memory exceeds the 227 KB per-CTA limit");
 
-__global__ void __launch_bounds__(128, 1) color_tc_kernel(const ColorParams p) {
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_kernel(const ColorParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemC& sm = *reinterpret_cast<SmemC*>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) { mbar_init(&sm.bar_w, 1); mbar_init(&sm.bar_mma, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(&sm.tmem_base, 128);
-    for (int i = tid; i < HC; i += 128) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
+    const int n_super = (p.n_tiles + 1) >> 1;
+    const int n_my = n_super > pair ? (n_super - pair + n_pairs - 1) / n_pairs : 0;
+    if (tid == 0) {
+        mbar_init(&sm.bar_w, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&sm.a_ready[s], 8); mbar_init(&sm.acc_full[s], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc2(&sm.tmem_base, 256);
+    for (int i = tid; i < HC; i += 288) {
         sm.bias[0][i] = p.bc1[i]; sm.bias[1][i] = p.bc2[i]; sm.bias[2][i] = p.bc3[i];
         sm.w4[0][i] = p.wc4[i]; sm.w4[1][i] = p.wc4[HC + i]; sm.w4[2][i] = p.wc4[2 * HC + i];
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t tacc_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    if (tid == 0) {   // weights: one bulk copy each, once per CTA
-        mbar_arrive_expect_tx(&sm.bar_w, C1_BYTES + 2 * C2_BYTES);
-        bulk_g2s(sm.W1, p.wpack_c, C1_BYTES, &sm.bar_w);
-        bulk_g2s(sm.W2, p.wpack_c + C1_BYTES, C2_BYTES, &sm.bar_w);
-        bulk_g2s(sm.W3, p.wpack_c + C1_BYTES + C2_BYTES, C2_BYTES, &sm.bar_w);
+    if (tid == 0) {   // this CTA's halves of the weights: one bulk copy each, once
+        mbar_arrive_expect_tx(&sm.bar_w, C1H_BYTES + 2 * C2H_BYTES);
+        bulk_g2s(sm.W1, p.wpack_c + rank * C1H_BYTES, C1H_BYTES, &sm.bar_w);
+        bulk_g2s(sm.W2, p.wpack_c + C1_BYTES + rank * C2H_BYTES, C2H_BYTES, &sm.bar_w);
+        bulk_g2s(sm.W3, p.wpack_c + C1_BYTES + C2_BYTES + rank * C2H_BYTES, C2H_BYTES, &sm.bar_w);
     }
-    const uint32_t idesc = make_idesc_bf16(ROWS, HC);
-    uint32_t mma_phase = 0;
-    bool w_ready = false;
-    uint4* Arow = reinterpret_cast<uint4*>(sm.A + tid * 16);
     constexpr int SJ = SLAB / 16;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int si = tile * ROWS + tid;
-        int slot = -1;
-        if (si < p.S) {
-            slot = __ldg(p.sample_ids + si);
-            const uint4* f4 = reinterpret_cast<const uint4*>(p.F + (int64_t)si * HID);
+    if (warp < 8) {
+        // ===================================================== slot group: thread = sample row
+        const int s = warp >> 2, row = tid & 127;
+        const uint32_t tacc_lane = tmem + (uint32_t)(s * HC) + ((uint32_t)((warp & 3) * 32) << 16);
+        uint4* Arow = reinterpret_cast<uint4*>(sm.A[s] + row * 16);
+        uint32_t ph = 0;
+        bool w_ready = false;
+        for (int j = s; j < n_my; j += 2) {
+            const int si = (2 * (pair + j * n_pairs) + (int)rank) * ROWS + row;
+            int slot = -1;
+            if (si < p.S) {
+                slot = __ldg(p.sample_ids + si);
+                const uint4* f4 = reinterpret_cast<const uint4*>(p.F + (int64_t)si * HID);
 #pragma unroll 8
-            for (int j = 0; j < 32; j++) Arow[j * SJ] = __ldg(f4 + j);
-            const int ray = slot / p.SR;
-            const float rd[3] = {__ldg(p.dirs + 3 * (int64_t)ray), __ldg(p.dirs + 3 * (int64_t)ray + 1), __ldg(p.dirs + 3 * (int64_t)ray + 2)};
-            float v[3];
-            rot_w2c(p.cam, rd, v);
-            float t[32];              // ori=True layout minus the raw copy: [sin (d-major, f-minor) 12 | cos 12] (SM:305-306)
+                for (int q = 0; q < 32; q++) Arow[q * SJ] = __ldg(f4 + q);
+                const int ray = slot / p.SR;
+                const float rd[3] = {__ldg(p.dirs + 3 * (int64_t)ray), __ldg(p.dirs + 3 * (int64_t)ray + 1), __ldg(p.dirs + 3 * (int64_t)ray + 2)};
+                float v[3];
+                rot_w2c(p.cam, rd, v);
+                float t[32];              // ori=True layout minus the raw copy: [sin (d-major, f-minor) 12 | cos 12] (SM:305-306)
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                float q[8];
-                pe<4>(v[d], q);
+                for (int d = 0; d < 3; d++) {
+                    float q8[8];
+                    pe<4>(v[d], q8);
 #pragma unroll
-                for (int f = 0; f < 4; f++) { t[d * 4 + f] = q[2 * f]; t[12 + d * 4 + f] = q[2 * f + 1]; }
-            }
+                    for (int f = 0; f < 4; f++) { t[d * 4 + f] = q8[2 * f]; t[12 + d * 4 + f] = q8[2 * f + 1]; }
+                }
 #pragma unroll
-            for (int j = 24; j < 32; j++) t[j] = 0.f;
+                for (int q = 24; q < 32; q++) t[q] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 4; j++) Arow[(32 + j) * SJ] = pack8(t + 8 * j);
-        } else {
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                for (int q = 0; q < 4; q++) Arow[(32 + q) * SJ] = pack8(t + 8 * q);
+            } else {
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 4
-            for (int j = 0; j < 36; j++) Arow[j * SJ] = z;
-        }
-#pragma unroll 1
-        for (int L = 0; L < 3; L++) {
+                for (int q = 0; q < 36; q++) Arow[q * SJ] = z;
+            }
+            if (!w_ready) { mbar_wait(&sm.bar_w, 0); w_ready = true; }   // the issuer may read this CTA's weights once we say "ready"
             fence_proxy_async();
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                if (!w_ready) mbar_wait(&sm.bar_w, 0);
+            tc_fence_before();                                            // our tcgen05.ld of the previous tile are complete
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&sm.a_ready[s], 0);
+#pragma unroll 1
+            for (int L = 0; L < 3; L++) {
+                mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
                 tc_fence_after();
-                const uint32_t a_base = smem_u32(sm.A);
+                float r[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+                for (int c0 = 0; c0 < HC; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tacc_lane + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 32; q++) {
+                        const float x = v[q] + sm.bias[L][c0 + q];
+                        v[q] = fmaxf(x, x * p.slope);
+                    }
+                    if (L < 2) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) Arow[(c0 / 8 + q) * SJ] = pack8(v + 8 * q);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; q++) {
+                            r[0] = fmaf(v[q], sm.w4[0][c0 + q], r[0]); r[1] = fmaf(v[q], sm.w4[1][c0 + q], r[1]);
+                            r[2] = fmaf(v[q], sm.w4[2][c0 + q], r[2]);
+                        }
+                    }
+                }
+                if (L < 2) {
+                    fence_proxy_async();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&sm.a_ready[s], 0);
+                } else if (slot >= 0) {
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        const float x = r[q] + __ldg(p.bc4 + q);
+                        p.rgb[3 * (int64_t)slot + q] = (1.f / (1.f + __expf(-x))) * (1.f + 2.f * 0.001f) - 0.001f;   // SM:359
+                    }
+                }
+            }
+        }
+    } else if (rank == 0 && lane == 0) {
+        // ===================================================== MMA issuer (leader): the next layer of whichever slot is ready
+        const uint32_t idesc = make_idesc_bf16(2 * ROWS, HC);
+        const int tot[2] = {3 * ((n_my + 1) >> 1), 3 * (n_my >> 1)};
+        int step[2] = {0, 0};
+        uint32_t ph[2] = {0, 0};
+        uint32_t spins = 0;
+        while (step[0] < tot[0] || step[1] < tot[1]) {
+            bool any = false;
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                if (step[s] >= tot[s] || !mbar_test(&sm.a_ready[s], ph[s])) continue;
+                ph[s] ^= 1; any = true;
+                tc_fence_after();
+                const int L = step[s] % 3;
+                const uint32_t a_base = smem_u32(sm.A[s]);
                 const uint32_t b_base = smem_u32(L == 0 ? sm.W1 : (L == 1 ? sm.W2 : sm.W3));
                 const int nk = L == 0 ? KIN_PAD / 16 : HC / 16;
                 for (int ks = 0; ks < nk; ks++) {
                     const uint64_t ad = make_smem_desc(a_base + (uint32_t)(ks * 2 * SLAB), SLAB, 128);
-                    const uint64_t bd = make_smem_desc(b_base + (uint32_t)(ks * 2 * HC * 16), HC * 16, 128);
-                    mma_bf16(tmem, ad, bd, idesc, (uint32_t)(ks > 0));
+                    const uint64_t bd = make_smem_desc(b_base + (uint32_t)(ks * 2 * (HC / 2) * 16), (HC / 2) * 16, 128);
+                    mma_bf16_2cta(tmem + (uint32_t)(s * HC), ad, bd, idesc, (uint32_t)(ks > 0));
                 }
-                mma_commit(&sm.bar_mma);
+                mma_commit2(&sm.acc_full[s], 3);
+                step[s]++;
             }
-            w_ready = true;
-            mbar_wait(&sm.bar_mma, mma_phase); mma_phase ^= 1;
-            tc_fence_after();
-            float r[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int c0 = 0; c0 < HC; c0 += 32) {
-                float v[32];
-                tmem_ld32(tacc_lane + c0, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float x = v[j] + sm.bias[L][c0 + j];
-                    v[j] = fmaxf(x, x * p.slope);
-                }
-                if (L < 2) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) Arow[(c0 / 8 + j) * SJ] = pack8(v + 8 * j);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        r[0] = fmaf(v[j], sm.w4[0][c0 + j], r[0]); r[1] = fmaf(v[j], sm.w4[1][c0 + j], r[1]);
-                        r[2] = fmaf(v[j], sm.w4[2][c0 + j], r[2]);
-                    }
-                    if (p.C3 && slot >= 0) {
-                        uint4* dst = reinterpret_cast<uint4*>(p.C3 + (int64_t)si * HC + c0);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) dst[j] = pack8(v + 8 * j);
-                    }
-                }
-            }
-            if (L == 2 && slot >= 0) {
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const float x = r[j] + __ldg(p.bc4 + j);
-                    p.rgb[3 * (int64_t)slot + j] = (1.f / (1.f + __expf(-x))) * (1.f + 2.f * 0.001f) - 0.001f;   // SM:359
-                }
-            }
+            if (!any) { __nanosleep(40); if (++spins > (1u << 26)) __trap(); }
         }
-        tc_fence_before();
-        __syncthreads();     // the next tile overwrites A and the accumulator
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    cluster_sync_all();
+    if (warp == 8) tmem_dealloc2(tmem, 256);
 }
 
 // ---------------------------------------------------------------------------------------------- weight packing
@@ -774,10 +815,12 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackJobs jobs, uint8_
         const int k = i % jb.kpad, n = i / jb.kpad;
         const float v = k < jb.in ? jb.w[(int64_t)n * jb.in + k] : 0.f;
         __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst + jb.dst_off);
-        if (jb.split) {   // field layers: 48-k chunks of [N-half 2][k-slab <=6][128 features][8]: a CTA of a pair bulk-copies one half
+        if (jb.split == 1) {   // field layers: 48-k chunks of [N-half 2][k-slab <=6][128 features][8]: a CTA of a pair bulk-copies one half
             const int ks = k >> 3, h = n >> 7, c = ks / CHUNK_SLABS;
             const int nsl = jb.kpad / 8 - CHUNK_SLABS * c < CHUNK_SLABS ? jb.kpad / 8 - CHUNK_SLABS * c : CHUNK_SLABS;
             d[(int64_t)c * (CHUNK_BYTES / 2) + ((int64_t)h * nsl + (ks - c * CHUNK_SLABS)) * 1024 + (n & 127) * 8 + (k & 7)] = __float2bfloat16(v);
+        } else if (jb.split == 2) {   // colour layers: two resident N-halves of k-slabs [k/8][64 features][8]
+            d[(((int64_t)(n >> 6) * (jb.kpad >> 3) + (k >> 3)) * 64 + (n & 63)) * 8 + (k & 7)] = __float2bfloat16(v);
         } else {
             d[((int64_t)(k >> 3) * jb.out + n) * 8 + (k & 7)] = __float2bfloat16(v);
         }
@@ -809,9 +852,9 @@ extern "C" int pnerf_tc_pack_weights(const pnerf_mlp* mlp, void* wpack, void* st
     jobs.j[1] = {mlp->w2, 256, 256, 256, (int64_t)layer_byte0(1), 1};
     jobs.j[2] = {mlp->w3, 256, 263, 288, (int64_t)layer_byte0(2), 1};
     jobs.j[3] = {mlp->w4, 256, 256, 256, (int64_t)layer_byte0(3), 1};
-    jobs.j[4] = {mlp->wc1, 128, 280, 288, (int64_t)WPACK_FIELD_BYTES, 0};
-    jobs.j[5] = {mlp->wc2, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES, 0};
-    jobs.j[6] = {mlp->wc3, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES + C2_BYTES, 0};
+    jobs.j[4] = {mlp->wc1, 128, 280, 288, (int64_t)WPACK_FIELD_BYTES, 2};
+    jobs.j[5] = {mlp->wc2, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES, 2};
+    jobs.j[6] = {mlp->wc3, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES + C2_BYTES, 2};
     for (int i = 0; i < 7; i++) if (!jobs.j[i].w) return PNERF_ERR_ARG;
     pack_weights_kernel<<<dim3(64, 7), 256, 0, (cudaStream_t)stream>>>(jobs, (uint8_t*)wpack);
     PNERF_LAUNCH_CHECK();
@@ -858,11 +901,12 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     c.wpack_c = (const uint8_t*)wpack + WPACK_FIELD_BYTES;
     c.bc1 = mlp->bc1; c.bc2 = mlp->bc2; c.bc3 = mlp->bc3; c.wc4 = mlp->wc4; c.bc4 = mlp->bc4;
     c.cam = p.cam; c.S = S; c.SR = SR; c.n_tiles = (S + ROWS - 1) / ROWS;
-    c.slope = mode->lrelu_slope; c.rgb = rgb; c.C3 = nullptr;
-    const int cgrid = c.n_tiles < kSMs ? c.n_tiles : kSMs;
+    c.slope = mode->lrelu_slope; c.rgb = rgb;
+    const int c_super = (c.n_tiles + 1) / 2;
+    const int cgrid = 2 * (c_super < kSMs / 2 ? c_super : kSMs / 2);   // CTA pairs
     const size_t csmem = sizeof(SmemC);
     PNERF_CUDA(cudaFuncSetAttribute(color_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-    color_tc_kernel<<<cgrid, 128, csmem, st>>>(c);
+    color_tc_kernel<<<cgrid, 288, csmem, st>>>(c);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }
