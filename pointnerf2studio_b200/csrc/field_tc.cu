@@ -53,6 +53,10 @@ constexpr int N_UNITS = 34;                      // 32-k units of 16 KB in the p
 // EPW 8 (832 threads, 72 registers, spills): 17.5 ms although a tile encodes in 4.5 k instead of 7.4 k clk; ENC_PARTS 2 / EPW 4:
 // 19.3 ms.  More warps do not shorten the epilogues -- the roles contend for issue slots in bursts -- so instructions, not
 // warps, are what the next version has to cut.
+#ifndef PNERF_STAGGER
+#define PNERF_STAGGER 1
+#endif
+constexpr int STAGGER = PNERF_STAGGER;           // layers by which slot 1 trails slot 0 (field kernels of the render bench: 0 -> 16.0 ms, 1 -> 14.3 ms, 2 -> 16.0 ms, 3 -> 15.8 ms)
 constexpr int ENC_PARTS = 1;                     // threads per row in the encoder: 1 (4 warps) or 2 (8 warps)
 constexpr int EPW = 8;                           // epilogue warps per slot: 4 (a warp drains all 256 columns of its 32 lanes) or 8 (128 each)
 constexpr int ENCW = 4 * ENC_PARTS;
@@ -371,7 +375,7 @@ __device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)
 template <int KP, bool SAVE>
 __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_t tacc_lane, const float* __restrict__ bias,
                                                    const float* __restrict__ wa, Meta& meta, SlotScratch& scr, int tile, int row, int half,
-                                                   int bar_id) {
+                                                   int bar_id, uint64_t* acc_empty) {
     uint4* gh4 = SAVE ? reinterpret_cast<uint4*>(p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)SAVE_H4 * SLAB + row * 16) : nullptr;
     constexpr int SPT = ROWS / KP;
     const int lane = threadIdx.x & 31, gl = lane % KP;
@@ -394,6 +398,13 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
         tmem_ld32(tacc_lane + cbeg + 96, vb);
         aggregate_chunk<KP, SAVE>(p, va, bias, wa, w, dot, slot, si, cbeg + 64, lane, gh4);
         tmem_ld_wait();
+        if (cbeg + HID / 2 >= (EPW == 8 ? (half + 1) * (HID / 2) : HID)) {
+            // this warp's last TMEM load has landed: the accumulator may be overwritten by the slot's next tile while the last
+            // chunk is still being reduced and stored (the aggregation epilogue is what gates a tile boundary)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(acc_empty, 0);
+        }
         aggregate_chunk<KP, SAVE>(p, vb, bias, wa, w, dot, slot, si, cbeg + 96, lane, gh4);
     }
     // combine the two column halves of the density head: the upper-half warp hands its partial dot to the lower-half warp
@@ -426,9 +437,9 @@ __host__ __device__ constexpr int chunk_slabs(int L, int c) {
 template <class F>
 __device__ __forceinline__ void for_each_step(int n_my, F&& fn) {
     const int n0 = 4 * ((n_my + 1) >> 1), n1 = 4 * (n_my >> 1);
-    const int n = n0 > n1 + 2 ? n0 : n1 + 2;
+    const int n = n0 > n1 + STAGGER ? n0 : n1 + STAGGER;
     for (int a = 0; a < n; a++) {
-        if (a >= 2 && a - 2 < n1) fn(1, (a - 2) & 3, (a - 2) >> 2);
+        if (a >= STAGGER && a - STAGGER < n1) fn(1, (a - STAGGER) & 3, (a - STAGGER) >> 2);
         if (a < n0) fn(0, a & 3, a >> 2);
     }
 }
@@ -530,10 +541,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
             mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
             tc_fence_after();
             tr.ev(13);
-            epilogue_aggregate<KP, SAVE>(p, tacc_lane, p.b4, p.wa, meta, sm.scratch[s], tile, row, half, 1 + s * 4 + (warp & 3));
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(&sm.acc_empty[s], 0);
+            epilogue_aggregate<KP, SAVE>(p, tacc_lane, p.b4, p.wa, meta, sm.scratch[s], tile, row, half, 1 + s * 4 + (warp & 3),
+                                         &sm.acc_empty[s]);
             tr.ev(23);
         }
     } else if (warp == ENCW + 2 * EPW) {
