@@ -57,8 +57,14 @@ constexpr int N_UNITS = 34;                      // 32-k units of 16 KB in the p
 #define PNERF_STAGGER 1
 #endif
 constexpr int STAGGER = PNERF_STAGGER;           // layers by which slot 1 trails slot 0 (field kernels of the render bench: 0 -> 16.0 ms, 1 -> 14.3 ms, 2 -> 16.0 ms, 3 -> 15.8 ms)
-constexpr int ENC_PARTS = 1;                     // threads per row in the encoder: 1 (4 warps) or 2 (8 warps)
-constexpr int EPW = 8;                           // epilogue warps per slot: 4 (a warp drains all 256 columns of its 32 lanes) or 8 (128 each)
+#ifndef PNERF_ENC_PARTS
+#define PNERF_ENC_PARTS 1
+#endif
+#ifndef PNERF_EPW
+#define PNERF_EPW 8
+#endif
+constexpr int ENC_PARTS = PNERF_ENC_PARTS;       // threads per row in the encoder: 1 (4 warps) or 2 (8 warps)
+constexpr int EPW = PNERF_EPW;                           // epilogue warps per slot: 4 (a warp drains all 256 columns of its 32 lanes) or 8 (128 each)
 constexpr int ENCW = 4 * ENC_PARTS;
 constexpr int NT = (ENCW + 2 * EPW + 2) * 32;    // encoder + 2 x EPW epilogue + producer + issuer warps
 constexpr int MAX_SPT = 16;                      // samples per tile at KP = 8
