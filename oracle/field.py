@@ -172,7 +172,8 @@ def field_forward(g, W: FieldWeights, Rw2c, mode="plugin", freqs=(3, 5, 4), bf16
     rnd = bf16_st if bf16 else (lambda t: t)
 
     def lin_r(name, x):
-        return F.linear(rnd(x), rnd(W.p[name + ".weight"]), W.p[name + ".bias"])
+        # the kernel carries the bias as a bf16 weight column multiplying a constant-1 operand column (fp32 accumulation)
+        return F.linear(rnd(x), rnd(W.p[name + ".weight"]), rnd(W.p[name + ".bias"]))
 
     assert mode in ("plugin", "original")
     ff, fd, fv = freqs

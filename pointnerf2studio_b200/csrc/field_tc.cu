@@ -48,7 +48,10 @@ constexpr int CHUNK_K = CHUNK_SLABS * 8;
 constexpr int CHUNK_BYTES = CHUNK_K * HID * 2;   // 24576 for the pair
 constexpr int HALF_BYTES = CHUNK_BYTES / 2;      // 12288: what one CTA loads per full chunk: 6 slabs x 128 output features
 constexpr int NGRP = 3;
-constexpr int N_UNITS = 34;                      // 32-k units of 16 KB in the packed buffer: 9 + 8 + 9 + 8
+// Biases ride in the GEMMs: every layer's A operand carries a constant-1 column (x0: pad column 284; h1 / h3: an extra k-slab,
+// K = 272; x3: pad column 263) and the packed weights carry the bias in that column, so no epilogue adds a bias (-40 of the
+// ~143 instructions per 32 accumulator columns) at the price of one more MMA in the two 256-wide layers.
+constexpr int BIAS_COL[4] = {284, 256, 263, 256};
 // Warp budget.  Measured (render bench, field kernels): ENC_PARTS 1 / EPW 8 (704 threads, 80 registers): 16.6 ms; ENC_PARTS 2 /
 // EPW 8 (832 threads, 72 registers, spills): 17.5 ms although a tile encodes in 4.5 k instead of 7.4 k clk; ENC_PARTS 2 / EPW 4:
 // 19.3 ms.  More warps do not shorten the epilogues -- the roles contend for issue slots in bursts -- so instructions, not
@@ -73,7 +76,7 @@ constexpr int MAX_SPT = 16;                      // samples per tile at KP = 8
 constexpr int HC = 128;
 constexpr int C1_BYTES = (KIN_PAD / 8) * HC * 16;   // 73728: Wc1 128 x 288
 constexpr int C2_BYTES = (HC / 8) * HC * 16;        // 32768: Wc2 / Wc3 128 x 128
-constexpr int WPACK_FIELD_BYTES = N_UNITS * 16384;                         // 557056
+constexpr int WPACK_FIELD_BYTES = (36 + 34 + 36 + 34) * HID * 16;          // 573440
 constexpr int WPACK_BYTES = WPACK_FIELD_BYTES + C1_BYTES + 2 * C2_BYTES;   // 696320
 
 struct Cam { float o[3]; float Rc[9]; float Rw[9]; };
@@ -245,7 +248,8 @@ __device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int 
             float t[64];
 #pragma unroll
             for (int c = 0; c < 6; c++) pe<5>(d[c], t + 10 * c);
-            t[60] = t[61] = t[62] = t[63] = 0.f;
+            t[60] = 1.f;                           // column 284: the constant that carries mlp_base.layers.0's bias
+            t[61] = t[62] = t[63] = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; j++) A.put(28 + j, pack8(t + 8 * j));
         } else {
@@ -261,6 +265,7 @@ __device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int 
             ex[0] = col[0]; ex[1] = col[1]; ex[2] = col[2];
             ex[3] = dr[0] - v[0]; ex[4] = dr[1] - v[1]; ex[5] = dr[2] - v[2];
             ex[6] = dr[0] * v[0] + dr[1] * v[1] + dr[2] * v[2];                                 // SM:334
+            ex[7] = 1.f;                                                                        // column 263: carries mlp_head.layers.0's bias
         }
     } else {
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -289,36 +294,28 @@ __device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int 
 // tcgen05.ld takes ~210 clk while the tensor pipe works on the other slot (60 clk idle; tools/tc_microbench.py), so the load
 // of chunk i+1 is issued before chunk i is processed (tcgen05.wait::ld waits for every outstanding load, hence the order).
 template <bool SAVE>
-__device__ __forceinline__ void epilogue_chunk_store(float (&v)[32], const float* __restrict__ bias, float slope, const RowSink<SAVE>& A, int c0) {
+__device__ __forceinline__ void epilogue_chunk_store(float (&v)[32], float slope, const RowSink<SAVE>& A, int c0) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));   // same address in every lane: one L1 transaction
-        float x;
-        x = v[j] + b.x; v[j] = fmaxf(x, x * slope);
-        x = v[j + 1] + b.y; v[j + 1] = fmaxf(x, x * slope);
-        x = v[j + 2] + b.z; v[j + 2] = fmaxf(x, x * slope);
-        x = v[j + 3] + b.w; v[j + 3] = fmaxf(x, x * slope);
-    }
+    for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], v[j] * slope);       // the bias is already in the accumulator
 #pragma unroll
     for (int j = 0; j < 4; j++) A.put(c0 / 8 + j, pack8(v + 8 * j));
 }
 template <bool SAVE>
-__device__ __forceinline__ void epilogue_store(uint32_t tacc_lane, const float* __restrict__ bias, float slope, uint8_t* Abuf,
-                                               uint8_t* gsave, int row, int cbeg) {
+__device__ __forceinline__ void epilogue_store(uint32_t tacc_lane, float slope, uint8_t* Abuf, uint8_t* gsave, int row, int cbeg) {
     const RowSink<SAVE> Arow{reinterpret_cast<uint4*>(Abuf + row * 16), reinterpret_cast<uint4*>(gsave + row * 16)};
     float va[32], vb[32];
     tmem_ld32(tacc_lane + cbeg, va);
     tmem_ld_wait();
     tmem_ld32(tacc_lane + cbeg + 32, vb);
-    epilogue_chunk_store<SAVE>(va, bias, slope, Arow, cbeg);
+    epilogue_chunk_store<SAVE>(va, slope, Arow, cbeg);
     tmem_ld_wait();
     tmem_ld32(tacc_lane + cbeg + 64, va);
-    epilogue_chunk_store<SAVE>(vb, bias, slope, Arow, cbeg + 32);
+    epilogue_chunk_store<SAVE>(vb, slope, Arow, cbeg + 32);
     tmem_ld_wait();
     tmem_ld32(tacc_lane + cbeg + 96, vb);
-    epilogue_chunk_store<SAVE>(va, bias, slope, Arow, cbeg + 64);
+    epilogue_chunk_store<SAVE>(va, slope, Arow, cbeg + 64);
     tmem_ld_wait();
-    epilogue_chunk_store<SAVE>(vb, bias, slope, Arow, cbeg + 96);
+    epilogue_chunk_store<SAVE>(vb, slope, Arow, cbeg + 96);
 }
 
 // sum over the KP lanes of a neighbour group of 32 per-lane values; afterwards lane gl (position in its group)
@@ -343,20 +340,18 @@ __device__ __forceinline__ void butterfly(float* a, int lane) {
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
 template <int KP, bool SAVE>
-__device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)[32], const float* __restrict__ bias,
-                                                const float* __restrict__ wa, float w, float& dot, int slot, int si, int c0, int lane,
-                                                uint4* gh4) {
+__device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)[32], const float* __restrict__ wa, float w, float& dot,
+                                                int slot, int si, int c0, int lane, uint4* gh4) {
     constexpr int VPL = 32 / KP;
     const int gl = lane % KP;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
         const float4 a = __ldg(reinterpret_cast<const float4*>(wa + c0 + j));
         float x;
-        x = v[j] + b.x; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.x, dot); v[j] = x;
-        x = v[j + 1] + b.y; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.y, dot); v[j + 1] = x;
-        x = v[j + 2] + b.z; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.z, dot); v[j + 2] = x;
-        x = v[j + 3] + b.w; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.w, dot); v[j + 3] = x;
+        x = v[j]; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.x, dot); v[j] = x;
+        x = v[j + 1]; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.y, dot); v[j + 1] = x;
+        x = v[j + 2]; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.z, dot); v[j + 2] = x;
+        x = v[j + 3]; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.w, dot); v[j + 3] = x;
     }
     if (SAVE) {
 #pragma unroll
@@ -379,9 +374,8 @@ __device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)
 }
 
 template <int KP, bool SAVE>
-__device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_t tacc_lane, const float* __restrict__ bias,
-                                                   const float* __restrict__ wa, Meta& meta, SlotScratch& scr, int tile, int row, int half,
-                                                   int bar_id, uint64_t* acc_empty) {
+__device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_t tacc_lane, const float* __restrict__ wa, Meta& meta,
+                                                   SlotScratch& scr, int tile, int row, int half, int bar_id, uint64_t* acc_empty) {
     uint4* gh4 = SAVE ? reinterpret_cast<uint4*>(p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)SAVE_H4 * SLAB + row * 16) : nullptr;
     constexpr int SPT = ROWS / KP;
     const int lane = threadIdx.x & 31, gl = lane % KP;
@@ -396,13 +390,13 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
         tmem_ld32(tacc_lane + cbeg, va);
         tmem_ld_wait();
         tmem_ld32(tacc_lane + cbeg + 32, vb);
-        aggregate_chunk<KP, SAVE>(p, va, bias, wa, w, dot, slot, si, cbeg, lane, gh4);
+        aggregate_chunk<KP, SAVE>(p, va, wa, w, dot, slot, si, cbeg, lane, gh4);
         tmem_ld_wait();
         tmem_ld32(tacc_lane + cbeg + 64, va);
-        aggregate_chunk<KP, SAVE>(p, vb, bias, wa, w, dot, slot, si, cbeg + 32, lane, gh4);
+        aggregate_chunk<KP, SAVE>(p, vb, wa, w, dot, slot, si, cbeg + 32, lane, gh4);
         tmem_ld_wait();
         tmem_ld32(tacc_lane + cbeg + 96, vb);
-        aggregate_chunk<KP, SAVE>(p, va, bias, wa, w, dot, slot, si, cbeg + 64, lane, gh4);
+        aggregate_chunk<KP, SAVE>(p, va, wa, w, dot, slot, si, cbeg + 64, lane, gh4);
         tmem_ld_wait();
         if (cbeg + HID / 2 >= (EPW == 8 ? (half + 1) * (HID / 2) : HID)) {
             // this warp's last TMEM load has landed: the accumulator may be overwritten by the slot's next tile while the last
@@ -411,7 +405,7 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(acc_empty, 0);
         }
-        aggregate_chunk<KP, SAVE>(p, vb, bias, wa, w, dot, slot, si, cbeg + 96, lane, gh4);
+        aggregate_chunk<KP, SAVE>(p, vb, wa, w, dot, slot, si, cbeg + 96, lane, gh4);
     }
     // combine the two column halves of the density head: the upper-half warp hands its partial dot to the lower-half warp
     float dot_other = 0.f;
@@ -430,9 +424,9 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
     if (gl == 0 && slot >= 0) p.sigma[slot] = sg;                           // SM:344
 }
 
-__host__ __device__ constexpr int layer_slabs(int L) { return (L & 1) ? 32 : 36; }     // 8-wide k-slabs of the layer (K = 256 / 288)
-__host__ __device__ constexpr int layer_chunks(int L) { return (void)L, 6; }            // 48-k chunks: 288 = 6 x 48, 256 = 5 x 48 + 16
-__host__ __device__ constexpr int layer_byte0(int L) { return 16384 * (L == 0 ? 0 : (L == 1 ? 9 : (L == 2 ? 17 : 26))); }
+__host__ __device__ constexpr int layer_slabs(int L) { return (L & 1) ? 34 : 36; }     // 8-wide k-slabs of the layer (K = 272 / 288)
+__host__ __device__ constexpr int layer_chunks(int L) { return (void)L, 6; }            // 48-k chunks: 288 = 6 x 48, 272 = 5 x 48 + 32
+__host__ __device__ constexpr int layer_byte0(int L) { return HID * 16 * (L == 0 ? 0 : (L == 1 ? 36 : (L == 2 ? 70 : 106))); }
 __host__ __device__ constexpr int chunk_slabs(int L, int c) {
     return layer_slabs(L) - CHUNK_SLABS * c < CHUNK_SLABS ? layer_slabs(L) - CHUNK_SLABS * c : CHUNK_SLABS;
 }
@@ -522,18 +516,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
                 // layer L's output is the next layer's A operand: H1 (L=0), X3 = [H2 | extras] (L=1), H3 (L=2)
                 uint8_t* gsave = SAVE ? p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)(L == 0 ? SAVE_H1 : (L == 1 ? SAVE_X3 : SAVE_H3)) * SLAB
                                       : nullptr;
-                const float* bias = L == 0 ? p.b1 : (L == 1 ? p.b2 : p.b3);
                 if (EPW == 8) {
-                    epilogue_store<SAVE>(tacc_lane, bias, p.slope, sm.A[s], gsave, row, half * (HID / 2));
+                    epilogue_store<SAVE>(tacc_lane, p.slope, sm.A[s], gsave, row, half * (HID / 2));
                 } else {
-                    epilogue_store<SAVE>(tacc_lane, bias, p.slope, sm.A[s], gsave, row, 0);
-                    epilogue_store<SAVE>(tacc_lane, bias, p.slope, sm.A[s], gsave, row, HID / 2);
+                    epilogue_store<SAVE>(tacc_lane, p.slope, sm.A[s], gsave, row, 0);
+                    epilogue_store<SAVE>(tacc_lane, p.slope, sm.A[s], gsave, row, HID / 2);
                 }
-                if (L == 1 && (half || EPW == 4)) {   // layer-3 input columns 256..287: the 7 per-row extras, then zeros
-                    const RowSink<SAVE> A{reinterpret_cast<uint4*>(sm.A[s] + row * 16), reinterpret_cast<uint4*>(gsave + row * 16)};
-                    A.put(32, sm.scratch[s].extras[row]);
+                if (half || EPW == 4) {
                     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-                    A.put(33, z); A.put(34, z); A.put(35, z);
+                    if (L == 1) {   // layer-3 input columns 256..287: the 7 per-row extras and the constant 1 (bias column 263), then zeros
+                        const RowSink<SAVE> A{reinterpret_cast<uint4*>(sm.A[s] + row * 16), reinterpret_cast<uint4*>(gsave + row * 16)};
+                        A.put(32, sm.scratch[s].extras[row]);
+                        A.put(33, z); A.put(34, z); A.put(35, z);
+                    } else {        // layers 2 and 4 (K = 272): column 256 = 1 carries the bias, 257..271 = 0 (not part of the saved tile)
+                        uint4* Arow = reinterpret_cast<uint4*>(sm.A[s] + row * 16);
+                        Arow[32 * (SLAB / 16)] = make_uint4(0x00003F80u, 0u, 0u, 0u);
+                        Arow[33 * (SLAB / 16)] = z;
+                    }
                 }
                 fence_proxy_async();
                 tc_fence_before();
@@ -547,7 +546,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
             mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
             tc_fence_after();
             tr.ev(13);
-            epilogue_aggregate<KP, SAVE>(p, tacc_lane, p.b4, p.wa, meta, sm.scratch[s], tile, row, half, 1 + s * 4 + (warp & 3),
+            epilogue_aggregate<KP, SAVE>(p, tacc_lane, p.wa, meta, sm.scratch[s], tile, row, half, 1 + s * 4 + (warp & 3),
                                          &sm.acc_empty[s]);
             tr.ev(23);
         }
@@ -820,7 +819,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
 
 // ---------------------------------------------------------------------------------------------- weight packing
 // fp32 nn.Linear weights (out,in) -> bf16 K-slab layout [k/8][out][8], K zero-padded; 34 field chunks then Wc1, Wc2, Wc3.
-struct PackJob { const float* w; int out, in, kpad; int64_t dst_off; int split; };
+struct PackJob { const float* w; int out, in, kpad; int64_t dst_off; int split; const float* bias; int bias_col; };
 struct PackJobs { PackJob j[7]; };
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(PackJobs jobs, uint8_t* __restrict__ dst) {
@@ -828,7 +827,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackJobs jobs, uint8_
     const int total = jb.out * jb.kpad;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int k = i % jb.kpad, n = i / jb.kpad;
-        const float v = k < jb.in ? jb.w[(int64_t)n * jb.in + k] : 0.f;
+        const float v = k < jb.in ? jb.w[(int64_t)n * jb.in + k] : ((jb.bias && k == jb.bias_col) ? jb.bias[n] : 0.f);
         __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst + jb.dst_off);
         if (jb.split == 1) {   // field layers: 48-k chunks of [N-half 2][k-slab <=6][128 features][8]: a CTA of a pair bulk-copies one half
             const int ks = k >> 3, h = n >> 7, c = ks / CHUNK_SLABS;
@@ -863,13 +862,14 @@ extern "C" int64_t pnerf_tc_wpack_bytes(void) { return WPACK_BYTES; }
 extern "C" int pnerf_tc_pack_weights(const pnerf_mlp* mlp, void* wpack, void* stream) {
     if (!mlp || !wpack) return PNERF_ERR_ARG;
     PackJobs jobs;
-    jobs.j[0] = {mlp->w1, 256, 284, 288, 0, 1};
-    jobs.j[1] = {mlp->w2, 256, 256, 256, (int64_t)layer_byte0(1), 1};
-    jobs.j[2] = {mlp->w3, 256, 263, 288, (int64_t)layer_byte0(2), 1};
-    jobs.j[3] = {mlp->w4, 256, 256, 256, (int64_t)layer_byte0(3), 1};
-    jobs.j[4] = {mlp->wc1, 128, 280, 288, (int64_t)WPACK_FIELD_BYTES, 2};
-    jobs.j[5] = {mlp->wc2, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES, 2};
-    jobs.j[6] = {mlp->wc3, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES + C2_BYTES, 2};
+    jobs.j[0] = {mlp->w1, 256, 284, 288, 0, 1, mlp->b1, BIAS_COL[0]};
+    jobs.j[1] = {mlp->w2, 256, 256, 272, (int64_t)layer_byte0(1), 1, mlp->b2, BIAS_COL[1]};
+    jobs.j[2] = {mlp->w3, 256, 263, 288, (int64_t)layer_byte0(2), 1, mlp->b3, BIAS_COL[2]};
+    jobs.j[3] = {mlp->w4, 256, 256, 272, (int64_t)layer_byte0(3), 1, mlp->b4, BIAS_COL[3]};
+    jobs.j[4] = {mlp->wc1, 128, 280, 288, (int64_t)WPACK_FIELD_BYTES, 2, nullptr, 0};
+    jobs.j[5] = {mlp->wc2, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES, 2, nullptr, 0};
+    jobs.j[6] = {mlp->wc3, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES + C2_BYTES, 2, nullptr, 0};
+    for (int i = 0; i < 4; i++) if (!jobs.j[i].bias) return PNERF_ERR_ARG;
     for (int i = 0; i < 7; i++) if (!jobs.j[i].w) return PNERF_ERR_ARG;
     pack_weights_kernel<<<dim3(64, 7), 256, 0, (cudaStream_t)stream>>>(jobs, (uint8_t*)wpack);
     PNERF_LAUNCH_CHECK();
