@@ -214,13 +214,19 @@ __device__ __forceinline__ void list_insert(float (&bd2)[KMAX], int (&bidx)[KMAX
     if (d2 < bd2[0]) { bd2[0] = d2; bidx[0] = idx; }
 }
 
+// Per shell the thread first lists its non-empty record runs (start, length) in shared memory, then the warp walks all
+// candidate streams in lock step: the trip count is the warp's longest stream and the sorted insertion runs branch-free
+// for every lane (a rejected or missing candidate carries d2 = +inf and changes nothing).  The nested per-run loops this
+// replaces executed sum_runs max_lane(len) iterations with a divergent 48-instruction insertion: 979 M warp instructions
+// for the render bench.
 template <int KMAX>
 __global__ void __launch_bounds__(128) query_kernel(Frame f, const int* __restrict__ cell_start,
                                                      const float4* __restrict__ recs, const float* __restrict__ sample_loc,
                                                      const int* __restrict__ sample_cnt, int R, int SR, int K, int layers,
-                                                     float r2, int* __restrict__ sample_pidx, uint8_t* __restrict__ sample_valid,
-                                                     unsigned long long* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
+                                                     float r2, int max_runs, int* __restrict__ sample_pidx,
+                                                     uint8_t* __restrict__ sample_valid, unsigned long long* __restrict__ stats) {
+    extern __shared__ int s_runs[];                    // [max_runs][2][128]: start / length of run j of thread t at (j*2 + {0,1})*128 + t
+    const int lane = threadIdx.x & 31, t = threadIdx.x;
     const int cpr = (SR + 31) >> 5;                    // 32-slot chunks per ray
     const int64_t n_tasks = (int64_t)R * cpr;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -228,18 +234,25 @@ __global__ void __launch_bounds__(128) query_kernel(Frame f, const int* __restri
     for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_tasks; w += warps) {
         const int r = (int)(w / cpr);
         const int slot = (int)(w % cpr) * 32 + lane;
-        if (slot >= SR) continue;
         const int64_t sid = (int64_t)r * SR + slot;
         float bd2[KMAX];
         int bidx[KMAX];
 #pragma unroll
         for (int i = 0; i < KMAX; i++) { bd2[i] = INFINITY; bidx[i] = -1; }
-        if (slot < __ldg(sample_cnt + r)) {
-            const float qx = __ldg(sample_loc + 3 * sid), qy = __ldg(sample_loc + 3 * sid + 1), qz = __ldg(sample_loc + 3 * sid + 2);
-            int vx, vy, vz;
-            if (voxel_of(f, qx, qy, qz, vx, vy, vz)) {
-                int seen = 0;
-                for (int shell = 0; shell < layers; shell++) {
+        const int cnt = __ldg(sample_cnt + r);
+        if ((int)(w % cpr) * 32 < cnt) {               // warp-uniform: some slot of this chunk is filled
+            float qx = 0.f, qy = 0.f, qz = 0.f;
+            int vx = 0, vy = 0, vz = 0;
+            bool searching = false;
+            if (slot < cnt && slot < SR) {
+                qx = __ldg(sample_loc + 3 * sid); qy = __ldg(sample_loc + 3 * sid + 1); qz = __ldg(sample_loc + 3 * sid + 2);
+                searching = voxel_of(f, qx, qy, qz, vx, vy, vz);
+            }
+            int seen = 0;
+            for (int shell = 0; shell < layers; shell++) {
+                // ---- phase 1: this thread's runs of the shell, in visit order (ux, uy, uz)
+                int nr = 0, total = 0;
+                if (searching) {
                     for (int dx = -shell; dx <= shell; dx++) {
                         const int x = vx + dx;
                         if (x < 0 || x >= f.dim[0]) continue;
@@ -259,33 +272,55 @@ __global__ void __launch_bounds__(128) query_kernel(Frame f, const int* __restri
                                 const int a = __ldg(cell_start + c0), b = __ldg(cell_start + c0 + (z1 - z0) + 1);
                                 n_vis += (unsigned long long)(z1 - z0 + 1);
                                 n_cand += (unsigned long long)(b - a);
-                                for (int i = a; i < b; i++) {
-                                    const float4 rec = __ldg(recs + i);
-                                    const float ex = __fsub_rn(rec.x, qx), ey = __fsub_rn(rec.y, qy), ez = __fsub_rn(rec.z, qz);
-                                    const float d2 = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));   // CU:271 as nvcc contracts it
-                                    if (r2 == 0.f || d2 <= r2) {
-                                        seen++;
-                                        if (d2 < bd2[KMAX - 1]) list_insert<KMAX>(bd2, bidx, d2, __float_as_int(rec.w) & 0x0fffffff);
-                                    }
+                                if (b > a) {
+                                    s_runs[(nr * 2) * 128 + t] = a;
+                                    s_runs[(nr * 2 + 1) * 128 + t] = b - a;
+                                    nr++; total += b - a;
                                 }
                             }
                         }
                     }
-                    if (seen >= K) break;   // CU:300
                 }
+                // ---- phase 2: all candidate streams of the warp in lock step
+                const int trips = __reduce_max_sync(0xffffffffu, total);
+                int run = 0, i = 0, rem = 0;
+                if (nr > 0) { i = s_runs[t]; rem = s_runs[128 + t]; }
+                for (int it = 0; it < trips; it++) {
+                    float d2 = INFINITY;
+                    int idx = -1;
+                    if (it < total) {
+                        const float4 rec = __ldg(recs + i);
+                        const float ex = __fsub_rn(rec.x, qx), ey = __fsub_rn(rec.y, qy), ez = __fsub_rn(rec.z, qz);
+                        const float dd = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));   // CU:271 as nvcc contracts it
+                        if (r2 == 0.f || dd <= r2) { seen++; d2 = dd; idx = __float_as_int(rec.w) & 0x0fffffff; }
+                        i++; rem--;
+                        if (rem == 0) {                          // next run of this thread's list
+                            run++;
+                            if (run < nr) {
+                                const int* e = s_runs + (run * 2) * 128 + t;
+                                i = e[0]; rem = e[128];
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, d2 < bd2[KMAX - 1])) list_insert<KMAX>(bd2, bidx, d2, idx);
+                }
+                if (seen >= K) searching = false;   // CU:300: this sample stops after the layer; the warp goes on for the others
+                if (!__any_sync(0xffffffffu, searching)) break;
             }
         }
-        int* out = sample_pidx + sid * K;
-        if (K == KMAX && (KMAX % 4) == 0) {
+        if (slot < SR) {
+            int* out = sample_pidx + sid * K;
+            if (K == KMAX && (KMAX % 4) == 0) {
 #pragma unroll
-            for (int i = 0; i < KMAX; i += 4)
-                *reinterpret_cast<int4*>(out + i) = make_int4(bidx[i], bidx[i + 1], bidx[i + 2], bidx[i + 3]);
-        } else {
+                for (int i = 0; i < KMAX; i += 4)
+                    *reinterpret_cast<int4*>(out + i) = make_int4(bidx[i], bidx[i + 1], bidx[i + 2], bidx[i + 3]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < KMAX; i++)
-                if (i < K) out[i] = bidx[i];
+                for (int i = 0; i < KMAX; i++)
+                    if (i < K) out[i] = bidx[i];
+            }
+            sample_valid[sid] = bidx[0] >= 0 ? 1 : 0;
         }
-        sample_valid[sid] = bidx[0] >= 0 ? 1 : 0;
     }
     if (stats) {
 #pragma unroll
@@ -295,6 +330,7 @@ __global__ void __launch_bounds__(128) query_kernel(Frame f, const int* __restri
         }
         if (lane == 0 && (n_vis | n_cand)) { atomicAdd(stats, n_vis); atomicAdd(stats + 1, n_cand); }
     }
+    (void)max_runs;
 }
 
 int ray_warps_grid(int R) {
@@ -368,8 +404,10 @@ extern "C" int pnerf_query(const pnerf_grid_view* g, const float* sample_loc, co
     const int blocks = (int)min((int64_t)kSMs * 16, (tasks * 32 + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* recs = (const float4*)g->recs;
+    const int max_runs = layers == 1 ? 1 : (layers == 2 ? 10 : 34);     // runs of the largest shell: 1, 8 + 2, 16 + 18
+    const size_t smem = (size_t)max_runs * 2 * 128 * sizeof(int);
 #define PNERF_LAUNCH_Q(KM) \
-    query_kernel<KM><<<blocks, 128, 0, st>>>(f, g->cell_start, recs, sample_loc, sample_cnt, R, SR, K, layers, r2, sample_pidx, sample_valid, stats)
+    query_kernel<KM><<<blocks, 128, smem, st>>>(f, g->cell_start, recs, sample_loc, sample_cnt, R, SR, K, layers, r2, max_runs, sample_pidx, sample_valid, stats)
     if (K <= 4) PNERF_LAUNCH_Q(4);
     else if (K <= 8) PNERF_LAUNCH_Q(8);
     else if (K <= 16) PNERF_LAUNCH_Q(16);
