@@ -249,6 +249,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))     # N ranks share the host cores
     import importlib.util
     from pointnerf2studio_b200 import PointNerf, PointNerfConfig, RayBundle, native
     precision = args.precision

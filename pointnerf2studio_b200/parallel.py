@@ -21,8 +21,14 @@ def shard_rays(n_rays: int, rank: int, world: int):
     return lo, min(lo + per, n_rays)
 
 
+LARGE = 1 << 20     # tensors with at least this many elements are reduced in place, the rest travel in one flat bucket
+
+
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], dist, average: bool = True) -> None:
-    """In-place sum (or mean) of `.grad` over all ranks through one flat fp32 bucket."""
+    """In-place sum (or mean) of `.grad` over all ranks.  The dense neural-point gradients (embedding: 128 B per point) are
+    reduced where they lie -- no flatten / unflatten copies of 156 B per point -- and the small MLP gradients share one flat
+    bucket; all collectives are issued asynchronously and waited for together.  With NCCL the mean is taken by the
+    collective itself (ReduceOp.AVG)."""
     params = [p for p in params if p.requires_grad]
     if not params:
         return
@@ -30,15 +36,28 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], dist, average: boo
     for p in params:
         if p.grad is None:
             p.grad = torch.zeros_like(p)
-    flat = torch.cat([p.grad.reshape(-1) for p in params])
-    dist.all_reduce(flat)
-    if average:
-        flat.div_(world)
-    off = 0
-    for p in params:
-        n = p.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p))
-        off += n
+    use_avg = average and dist.get_backend() == "nccl"
+    op = dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM
+    big = [p for p in params if p.grad.numel() >= LARGE and p.grad.is_contiguous()]
+    small = [p for p in params if not (p.grad.numel() >= LARGE and p.grad.is_contiguous())]
+    work = [dist.all_reduce(p.grad, op=op, async_op=True) for p in big]
+    flat = None
+    if small:
+        flat = torch.cat([p.grad.reshape(-1) for p in small])
+        work.append(dist.all_reduce(flat, op=op, async_op=True))
+    for w in work:
+        w.wait()
+    if average and not use_avg:
+        for p in big:
+            p.grad.div_(world)
+        if flat is not None:
+            flat.div_(world)
+    if flat is not None:
+        off = 0
+        for p in small:
+            n = p.numel()
+            p.grad.copy_(flat[off:off + n].view_as(p))
+            off += n
 
 
 def gather_pixels(local_rgb: torch.Tensor, local_mask: torch.Tensor, n_rays: int, dist):

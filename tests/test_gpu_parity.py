@@ -356,3 +356,21 @@ def test_probe_prune_grow(flow):
     xyz_new = npnts.points_xyz.detach().cpu().numpy()
     _, _, _, pidx_n, loc_n, mask_n, hit_n, _ = _oracle_query(xyz_new, cam, pix, SR, 8, 12, (3, 3, 3))
     np.testing.assert_array_equal(model.last_query_dense().sample_pidx.cpu().numpy(), pidx_n)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_model_all_rays_miss(precision):
+    """B.14 (i) through the model: a bundle whose rays all miss the cloud gives white pixels and an all-zero ray mask (SM:500-502),
+    in eval and in train mode (the hit-ray compaction leaves zero rows for every later stage)."""
+    s, cloud, cam, _ = _scene("tinyP")
+    pix = np.arange(96)                                   # image corner
+    model = _make_model(cloud, precision, "plugin", SR=16, K=4, P=3)
+    for train in (False, True):
+        model.train(train)
+        with torch.set_grad_enabled(train):
+            out = model.get_outputs(_bundle(cam, pix))
+        assert out["coarse_raycolor"].shape == (96, 3) and bool((out["coarse_raycolor"] == 1.0).all())
+        assert out["ray_mask"].shape == (96,) and int(out["ray_mask"].sum()) == 0
+    out = model.probe(_bundle(cam, pix))
+    assert float(out["ray_max_shading_opacity"].abs().sum()) == 0.0
+    assert model.get_outputs_for_camera_ray_bundle(_bundle(cam, pix), chunk=40)["coarse_raycolor"].shape == (96, 3)

@@ -29,13 +29,20 @@ def _worker(rank, world, port, out):
     if rank == 0:
         b.grad = torch.arange(7.0)                 # rank 1 has no grad for b (unused parameter)
     parallel.allreduce_gradients([a, b, c], dist)
+    # the in-place path of large tensors (the dense neural-point gradients): same result as the flat bucket
+    d = torch.nn.Parameter(torch.zeros(6, 4))
+    e = torch.nn.Parameter(torch.zeros(3))
+    d.grad = torch.full((6, 4), float(10 * (rank + 1)))
+    e.grad = torch.full((3,), float(rank))
+    parallel.LARGE = 8
+    parallel.allreduce_gradients([d, e], dist)
     # render side: 10 rays split in row blocks
     lo, hi = parallel.shard_rays(10, rank, world)
     rgb = torch.arange(lo, hi, dtype=torch.float32)[:, None].expand(-1, 3).contiguous()
     mask = torch.ones(hi - lo, dtype=torch.int8) * (rank + 1)
     full_rgb, full_mask = parallel.gather_pixels(rgb, mask, 10, dist)
     if rank == 0:
-        torch.save({"a": a.grad, "b": b.grad, "rgb": full_rgb, "mask": full_mask}, out)
+        torch.save({"a": a.grad, "b": b.grad, "d": d.grad, "e": e.grad, "rgb": full_rgb, "mask": full_mask}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,6 +53,8 @@ def test_allreduce_and_pixel_gather_world2(tmp_path):
     r = torch.load(out)
     torch.testing.assert_close(r["a"], torch.full((5, 3), 1.5))
     torch.testing.assert_close(r["b"], torch.arange(7.0) / 2)
+    torch.testing.assert_close(r["d"], torch.full((6, 4), 15.0))
+    torch.testing.assert_close(r["e"], torch.full((3,), 0.5))
     torch.testing.assert_close(r["rgb"][:, 0], torch.arange(10.0))
     assert r["mask"].tolist() == [1] * 5 + [2] * 5
 
