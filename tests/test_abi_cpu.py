@@ -106,3 +106,34 @@ def test_checkpoint_layout_roundtrip(tmp_path):
     assert back["neural_points.xyz"].shape == (len(cloud.xyz), 3)
     with pytest.raises(RuntimeError):
         checkpoint.load_point_cloud_checkpoint(tmp_path / "missing")
+
+
+def test_argument_errors_are_return_codes_not_crashes():
+    """Every entry validates its arguments before touching the device and reports through the return code (the reference's op
+    validates nothing, CPP:51-53): callable on a box without a GPU."""
+    import ctypes as C
+    from pointnerf2studio_b200 import _lib
+    lib = _lib.load()
+    ERR_ARG, OK = -1, 0
+    assert lib.pnerf_bbox(None, 10, None, None) == ERR_ARG
+    assert lib.pnerf_query(None, None, None, 4, 8, 8, 3, C.c_float(0.016), None, None, None, None) == ERR_ARG
+    g = _lib.GridView()
+    assert lib.pnerf_query(C.byref(g), None, None, 4, 8, 40, 3, C.c_float(0.016), None, None, None, None) == ERR_ARG      # K > 32
+    assert lib.pnerf_query(C.byref(g), None, None, 4, 8, 8, 9, C.c_float(0.016), None, None, None, None) == ERR_ARG       # 9^3 kernel
+    assert lib.pnerf_query(C.byref(g), None, None, 0, 8, 8, 3, C.c_float(0.016), None, None, None, None) == OK            # no rays
+    assert lib.pnerf_sample_select(C.byref(g), None, None, None, None, 0, 4, 400, 8, 1, None, None, None) == ERR_ARG
+    assert lib.pnerf_sample_select_jitter(C.byref(g), None, None, C.c_float(6.0), C.c_float(2.0), C.c_float(0.3), 1, 4, 400, 8, 1,
+                                          None, None, None) == ERR_ARG                                                     # far <= near
+    assert lib.pnerf_composite_forward(None, None, None, None, None, None, 4, 8, None, None, None, None) == ERR_ARG
+    cam, mode = _lib.Camera(), _lib.Mode()
+    assert lib.pnerf_composite_forward(C.byref(cam), C.byref(mode), None, None, None, None, 4, 200, None, None, None, None) == ERR_ARG  # SR > 128
+    assert lib.pnerf_composite_forward(C.byref(cam), C.byref(mode), None, None, None, None, 0, 8, None, None, None, None) == OK
+    pts, mlp = _lib.Points(), _lib.Mlp()
+    mode.lrelu_slope = 0.1
+    assert lib.pnerf_field_forward_tc(C.byref(pts), C.byref(cam), C.byref(mlp), None, C.byref(mode), None, None, None, None, 5, 8, 8,
+                                      None, None, None, 0, None) == ERR_ARG                                               # no packed weights
+    assert lib.pnerf_adam_step(None, 1, C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8), C.c_float(1.0), None) == ERR_ARG
+    assert lib.pnerf_adam_step(None, 0, C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8), C.c_float(1.0), None) == ERR_ARG
+    assert lib.pnerf_hit_rays(None, 0, None, None, None, 0, None) == ERR_ARG
+    assert lib.pnerf_tc_wpack_bytes() == 573440 + 73728 + 2 * 32768
+    assert lib.pnerf_field_tc_train_workspace_bytes(0, 8) > 0 and lib.pnerf_scan_workspace_bytes(1000) > 0
