@@ -228,7 +228,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="render", choices=["render", "train"])
+    ap.add_argument("--workload", default="render", choices=["render", "train", "scannet"])
     ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
     ap.add_argument("--points", type=int, default=N_POINTS)
     ap.add_argument("--cpu-rays", type=int, default=131072, help="pixels per step of the CPU arm")
@@ -257,9 +257,17 @@ def main():
         precision = "bf16" if importlib.util.find_spec("pointnerf2studio_b200.native_tc") is not None else "fp32"
     peaks = load_peaks()
 
-    cloud, t_cloud = make_scene(args.points)
     weights = make_weights()
-    cfg = PointNerfConfig(precision=precision)        # plugin defaults: SR=80, K=8, P=12, vsize .004 x vscale 2, jitter 0.3
+    if args.workload == "scannet":
+        # BASELINE configs[3]: ~3 M points, 1296 x 968 image, scaled voxel 0.016, radius 0.032, P = 30, SR = 24
+        # (dev_scripts/w_scannet_etf/scene101_points.sh:24-37); ONE image split in row blocks over the ranks + all-gather
+        from pointnerf2studio_b200.synth import make_cloud
+        cloud = make_cloud(3_000_000 if args.points == N_POINTS else args.points, seed=1237, scaled_vsize=0.016, P=30,
+                           radii=(0.5, 0.72, 0.93))
+        cfg = PointNerfConfig(precision=precision, vsize=[0.008] * 3, P=30, SR=24)
+    else:
+        cloud, t_cloud = make_scene(args.points)
+        cfg = PointNerfConfig(precision=precision)    # plugin defaults: SR=80, K=8, P=12, vsize .004 x vscale 2, jitter 0.3
     model = PointNerf(cfg, state_dict=cloud.state_dict())
     own = dict(model.named_parameters())
     with torch.no_grad():
@@ -268,7 +276,39 @@ def main():
     cam = view(rank)
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")     # 256 MB > 126 MB L2
 
-    if args.workload == "render":
+    if args.workload == "scannet":
+        from pointnerf2studio_b200.parallel import gather_interleaved_image, interleaved_rows
+        from pointnerf2studio_b200.synth import make_camera
+        model.eval()
+        cam = make_camera(H=968, W=1296, focal=1170.0, azim_deg=30.0, elev_deg=20.0)      # the same view on every rank
+        n_img = cam.H * cam.W
+        rows = np.asarray(interleaved_rows(cam.H, rank, world))                          # rows rank, rank + N, ...: balanced work
+        pix = (rows[:, None] * cam.W + np.arange(cam.W)[None]).reshape(-1)
+        host = host_bundle(cam, pix)
+        rb_dev = to_device(host, RayBundle)
+        R = len(pix)
+        out_host = torch.empty((n_img, 3), dtype=torch.float32).pin_memory()
+
+        def render_rows(rb):
+            o = model.get_outputs_for_camera_ray_bundle(rb)
+            if dist is None:
+                return o["coarse_raycolor"]
+            return gather_interleaved_image(o["coarse_raycolor"], cam.H, cam.W, dist)
+
+        def step_dev():
+            render_rows(rb_dev)
+
+        def step_e2e():
+            img = render_rows(to_device(host, RayBundle))
+            out_host[:img.shape[0]].copy_(img, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        d2h = out_host.numel() * 4
+        metric = "render rays/s"
+        workload = ("ScanNet-scale render: one 1296x968 image, rows interleaved over the ranks + pixel all-gather, 3M-point "
+                    "synthetic cloud, K=8, SR=24, voxel 0.016, P=30 (configs[3])")
+    elif args.workload == "render":
         model.eval()
         pix = np.arange(cam.H * cam.W)
         host = host_bundle(cam, pix)
@@ -365,7 +405,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = t.tolist()
-    rays_all = R * world * args.steps
+    rays_all = (n_img if args.workload == "scannet" else R * world) * args.steps
     value = rays_all / (ms_total * 1e-3)
     e2e_value = rays_all / (ms_e2e * 1e-3)
 
@@ -392,8 +432,9 @@ def main():
                             "algorithmic_bytes": q_bytes, "mean_voxels_visited": vis / max(filled, 1),
                             "mean_candidates": cand / max(filled, 1)}}
 
+    scaling = "strong" if args.workload == "scannet" else "weak"      # scannet: one image of fixed size shared by all ranks
     line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": workload, "n_points": int(cloud.xyz.shape[0]), "rays_per_step_per_gpu": R,
                        "rays_hit": rays_hit, "filled_slots": filled, "valid_samples_S": S, "neighbour_rows_M": M,
@@ -403,7 +444,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages}
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload != "scannet":
         n = args.cpu_rays
         cpu_arm(cloud, cam, weights, 256, cfg.SR, cfg.K)                        # warm-up (builds nothing that persists)
         dt, _ = cpu_arm(cloud, cam, weights, n, cfg.SR, cfg.K)

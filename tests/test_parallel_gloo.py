@@ -41,8 +41,12 @@ def _worker(rank, world, port, out):
     rgb = torch.arange(lo, hi, dtype=torch.float32)[:, None].expand(-1, 3).contiguous()
     mask = torch.ones(hi - lo, dtype=torch.int8) * (rank + 1)
     full_rgb, full_mask = parallel.gather_pixels(rgb, mask, 10, dist)
+    # interleaved row shards of a 5 x 4 image
+    rows = parallel.interleaved_rows(5, rank, world)
+    local = torch.tensor([[float(r * 4 + c)] * 3 for r in rows for c in range(4)])
+    img = parallel.gather_interleaved_image(local, 5, 4, dist)
     if rank == 0:
-        torch.save({"a": a.grad, "b": b.grad, "d": d.grad, "e": e.grad, "rgb": full_rgb, "mask": full_mask}, out)
+        torch.save({"img": img, "a": a.grad, "b": b.grad, "d": d.grad, "e": e.grad, "rgb": full_rgb, "mask": full_mask}, out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,6 +61,7 @@ def test_allreduce_and_pixel_gather_world2(tmp_path):
     torch.testing.assert_close(r["e"], torch.full((3,), 0.5))
     torch.testing.assert_close(r["rgb"][:, 0], torch.arange(10.0))
     assert r["mask"].tolist() == [1] * 5 + [2] * 5
+    torch.testing.assert_close(r["img"][:, 0], torch.arange(20.0))
 
 
 def test_shard_rays_covers_everything():
