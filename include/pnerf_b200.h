@@ -199,10 +199,10 @@ int pnerf_field_forward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h,
                            int64_t workspace_bytes, void* stream);
 
 /* Training on the tensor-core path.  Forward = pnerf_field_forward_tc for the per-neighbour networks with every MMA operand kept
- * in `workspace` (2.7 KB per neighbour row, tile layout of csrc/tc_layout.cuh), colour network in fp32.  Backward (what torch
+ * in `workspace` (2.7 KB per neighbour row + 1.3 KB per sample, tile layout of csrc/tc_layout.cuh).  Backward (what torch
  * autograd computes for the reference through SU:190-209, SM:270-359): consumes d sigma / d rgb (by slot) and the SAME workspace,
  * accumulates (+=) into the point gradients (may be NULL) and the MLP gradients: bf16 tcgen05 GEMMs for dgrad and wgrad of
- * mlp_base / mlp_head, fp32 accumulation.  `workspace` must be 256-byte aligned. */
+ * mlp_base / mlp_head / mlp_color, fp32 accumulation.  `workspace` must be 256-byte aligned. */
 int64_t pnerf_field_tc_train_workspace_bytes(int64_t n_samples, int K);
 int pnerf_field_forward_tc_train(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const void* wpack,
                                  const pnerf_mode* mode_h, const float* dirs, const float* sample_loc, const int* sample_pidx,
@@ -210,8 +210,9 @@ int pnerf_field_forward_tc_train(const pnerf_points* pts_h, const pnerf_camera* 
                                  int64_t workspace_bytes, void* stream);
 int pnerf_field_backward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const pnerf_mode* mode_h,
                             const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int n_samples,
-                            int SR, int K, const float* d_sigma, const float* d_rgb, float* g_embed, float* g_color, float* g_dir,
-                            float* g_conf, const pnerf_mlp_grad* g_mlp_h, void* workspace, int64_t workspace_bytes, void* stream);
+                            int SR, int K, const float* d_sigma, const float* d_rgb, const float* rgb /* forward output, by slot */,
+                            float* g_embed, float* g_color, float* g_dir, float* g_conf, const pnerf_mlp_grad* g_mlp_h, void* workspace,
+                            int64_t workspace_bytes, void* stream);
 
 /* Profiling hook: when `buf` (device, pnerf_tc_trace_bytes() bytes, zero-filled) is set, CTA 0 of the next field_tc launches
  * appends clock64-stamped pipeline events per role warp (tools/tc_trace.py decodes them).  NULL switches it off. */

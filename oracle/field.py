@@ -208,10 +208,13 @@ def field_forward(g, W: FieldWeights, Rw2c, mode="plugin", freqs=(3, 5, 4), bf16
     sigma = (a_hold.view(R2 * SR, K, 1) * wk).sum(-2)[vflat]             # SM:344
     f_hold = torch.zeros(R2 * SR * K, gfeat.shape[-1]).index_put((mflat.nonzero()[:, 0],), gfeat)
     Fs = (f_hold.view(R2 * SR, K, -1) * wk).sum(-2)[vflat]               # SM:348-353
-    cin = torch.cat([rnd(Fs), venc[vflat]], dim=-1)                       # SM:356
-    c = F.leaky_relu(W.lin("mlp_color.layers.0", cin), LRELU)
-    c = F.leaky_relu(W.lin("mlp_color.layers.1", c), LRELU)
-    c = F.leaky_relu(W.lin("mlp_color.layers.2", c), LRELU)
+    def lin_c(name, x):   # colour kernel: bf16 operands, fp32 bias added in the epilogue
+        return F.linear(rnd(x), rnd(W.p[name + ".weight"]), W.p[name + ".bias"])
+
+    cin = torch.cat([Fs, venc[vflat]], dim=-1)                            # SM:356
+    c = F.leaky_relu(lin_c("mlp_color.layers.0", cin), LRELU)
+    c = F.leaky_relu(lin_c("mlp_color.layers.1", c), LRELU)
+    c = F.leaky_relu(lin_c("mlp_color.layers.2", c), LRELU)
     rgb = torch.sigmoid(W.lin("field_output_color.net", c)) * (1 + 2 * 0.001) - 0.001        # SM:358-359
     dec = torch.zeros(R2 * SR, 4).index_put((vflat.nonzero()[:, 0],), torch.cat([sigma, rgb], dim=-1))
     extras = {"dists": dists, "weight": w, "weight_used": w_used, "conf_coefficient": conf_c,

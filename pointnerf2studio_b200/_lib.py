@@ -99,7 +99,7 @@ SIGNATURES = {
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pnerf_field_backward_tc": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.POINTER(Mode),
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(MlpGrad), C.c_void_p, C.c_int64, C.c_void_p]),
     "pnerf_tc_set_trace": (C.c_int, [C.c_void_p]),
     "pnerf_tc_trace_bytes": (C.c_int64, []),

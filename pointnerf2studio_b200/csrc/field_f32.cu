@@ -7,8 +7,6 @@
 // all-zero rows with zero aggregation weight, so they add nothing to any output or gradient (the
 // reference removes them with boolean indexing, SM:310-315).
 #include "pnerf_common.cuh"
-#include "tc_layout.cuh"
-#include <cuda_bf16.h>
 
 namespace pnerf {
 namespace {
@@ -498,70 +496,6 @@ int grid_warps(int64_t n_warps) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 }  // namespace
-}  // namespace pnerf
-
-// ---- fp32 colour network on bf16 aggregated features (tensor-core training path, see tc_layout.cuh)
-namespace pnerf {
-namespace {
-// One warp per sample: C0 = [float(F_s) 256 | PE(v) 24 | 0 x 8]
-__global__ void __launch_bounds__(256) color_input_kernel(Cam cam, const __nv_bfloat16* __restrict__ F, const float* __restrict__ dirs,
-                                                           const int* __restrict__ sample_ids, int S, int SR, float* __restrict__ C0) {
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < S; i += warps) {
-        float* c0 = C0 + (int64_t)i * LDC;
-#pragma unroll
-        for (int j = 0; j < HID / 32; j++) c0[lane + 32 * j] = __bfloat162float(F[(int64_t)i * HID + lane + 32 * j]);
-        const int ray = sample_ids[i] / SR;
-        const float rd[3] = {dirs[3 * ray], dirs[3 * ray + 1], dirs[3 * ray + 2]};
-        float v[3];
-        rot_w2c(cam, rd, v);
-        if (lane < 3 * F_VIEW) {
-            const int d = lane / F_VIEW, f = lane % F_VIEW;
-            float s, c;
-            sincosf(v[d] * (float)(1 << f), &s, &c);
-            c0[HID + lane] = s;
-            c0[HID + 3 * F_VIEW + lane] = c;
-        }
-        if (lane < LDC - INC) c0[INC + lane] = 0.f;
-    }
-}
-}  // namespace
-
-int64_t color_f32_ws_floats(int64_t S) { return S * (LDC + 3 * HC) + S * (3 * HC + LDC) + 64; }
-
-int color_forward_f32(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const pnerf_mode* mode, const float* dirs,
-                      const int* sample_ids, int S, int SR, const void* F_bf16, float* ws, float* rgb, cudaStream_t st) {
-    if (S == 0) return PNERF_OK;
-    const Cam c = make_cam(pts, cam);
-    float *C0 = ws, *C1 = C0 + (int64_t)S * LDC, *C2 = C1 + (int64_t)S * HC, *C3 = C2 + (int64_t)S * HC;
-    const float sl = mode->lrelu_slope;
-    color_input_kernel<<<grid_warps(S), 256, 0, st>>>(c, (const __nv_bfloat16*)F_bf16, dirs, sample_ids, S, SR, C0);
-    PNERF_LAUNCH_CHECK();
-    int rc;
-    if ((rc = linear_fwd(C0, LDC, mlp->wc1, mlp->bc1, C1, HC, S, HC, INC, sl, st))) return rc;
-    if ((rc = linear_fwd(C1, HC, mlp->wc2, mlp->bc2, C2, HC, S, HC, HC, sl, st))) return rc;
-    if ((rc = linear_fwd(C2, HC, mlp->wc3, mlp->bc3, C3, HC, S, HC, HC, sl, st))) return rc;
-    rgb_head_kernel<<<(S + 255) / 256, 256, 0, st>>>(C3, mlp->wc4, mlp->bc4, sample_ids, S, rgb);
-    PNERF_LAUNCH_CHECK();
-    return PNERF_OK;
-}
-
-int color_backward_f32(const pnerf_mlp* mlp, const pnerf_mlp_grad* gm, const pnerf_mode* mode, const int* sample_ids, int S,
-                       const float* d_rgb, float* ws, const float** dF, int* ldF, cudaStream_t st) {
-    float *C0 = ws, *C1 = C0 + (int64_t)S * LDC, *C2 = C1 + (int64_t)S * HC, *C3 = C2 + (int64_t)S * HC;
-    float *dC3 = C3 + (int64_t)S * HC, *dC2 = dC3 + (int64_t)S * HC, *dC1 = dC2 + (int64_t)S * HC, *dC0 = dC1 + (int64_t)S * HC;
-    *dF = dC0; *ldF = LDC;
-    if (S == 0) return PNERF_OK;
-    const float sl = mode->lrelu_slope;
-    int rc;
-    rgb_head_bwd_kernel<<<(S + 63) / 64, 128, 0, st>>>(C3, mlp->wc4, mlp->bc4, sample_ids, S, d_rgb, dC3, gm->wc4, gm->bc4);
-    PNERF_LAUNCH_CHECK();
-    if ((rc = linear_bwd(dC3, HC, C3, HC, C2, HC, mlp->wc3, gm->wc3, gm->bc3, dC2, HC, S, HC, HC, sl, st))) return rc;
-    if ((rc = linear_bwd(dC2, HC, C2, HC, C1, HC, mlp->wc2, gm->wc2, gm->bc2, dC1, HC, S, HC, HC, sl, st))) return rc;
-    if ((rc = linear_bwd(dC1, HC, C1, HC, C0, LDC, mlp->wc1, gm->wc1, gm->bc1, dC0, LDC, S, HC, INC, sl, st))) return rc;
-    return PNERF_OK;
-}
 }  // namespace pnerf
 
 using namespace pnerf;

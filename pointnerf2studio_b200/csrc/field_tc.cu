@@ -647,6 +647,7 @@ struct ColorParams {
     int S, SR, n_tiles;
     float slope;
     float* rgb;                    // (R*SR,3) by slot
+    uint8_t* csave;                // training: operand tiles [C0 | C1 | C2 | C3] per 128-sample tile (tc_layout.cuh), or NULL
 };
 
 constexpr int C1H_BYTES = C1_BYTES / 2, C2H_BYTES = C2_BYTES / 2;
@@ -671,6 +672,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   //
     return ok != 0;
 }
 
+template <bool SAVE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_kernel(const ColorParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemC& sm = *reinterpret_cast<SmemC*>(smem_raw);
@@ -709,13 +711,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
         uint32_t ph = 0;
         bool w_ready = false;
         for (int j = s; j < n_my; j += 2) {
-            const int si = (2 * (pair + j * n_pairs) + (int)rank) * ROWS + row;
+            const int ctile = 2 * (pair + j * n_pairs) + (int)rank;
+            const int si = ctile * ROWS + row;
+            uint4* grow = SAVE ? reinterpret_cast<uint4*>(p.csave + (int64_t)ctile * CSAVE_TILE_BYTES + row * 16) : nullptr;
             int slot = -1;
             if (si < p.S) {
                 slot = __ldg(p.sample_ids + si);
                 const uint4* f4 = reinterpret_cast<const uint4*>(p.F + (int64_t)si * HID);
 #pragma unroll 8
-                for (int q = 0; q < 32; q++) Arow[q * SJ] = __ldg(f4 + q);
+                for (int q = 0; q < 32; q++) {
+                    const uint4 fv = __ldg(f4 + q);
+                    Arow[q * SJ] = fv;
+                    if (SAVE) grow[q * SJ] = fv;
+                }
                 const int ray = slot / p.SR;
                 const float rd[3] = {__ldg(p.dirs + 3 * (int64_t)ray), __ldg(p.dirs + 3 * (int64_t)ray + 1), __ldg(p.dirs + 3 * (int64_t)ray + 2)};
                 float v[3];
@@ -731,11 +739,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
 #pragma unroll
                 for (int q = 24; q < 32; q++) t[q] = 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; q++) Arow[(32 + q) * SJ] = pack8(t + 8 * q);
+                for (int q = 0; q < 4; q++) {
+                    const uint4 pv = pack8(t + 8 * q);
+                    Arow[(32 + q) * SJ] = pv;
+                    if (SAVE) grow[(32 + q) * SJ] = pv;
+                }
             } else {
                 const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 4
-                for (int q = 0; q < 36; q++) Arow[q * SJ] = z;
+                for (int q = 0; q < 36; q++) {
+                    Arow[q * SJ] = z;
+                    if (SAVE) grow[q * SJ] = z;
+                }
             }
             if (!w_ready) { mbar_wait(&sm.bar_w, 0); w_ready = true; }   // the issuer may read this CTA's weights once we say "ready"
             fence_proxy_async();
@@ -756,6 +771,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
                     for (int q = 0; q < 32; q++) {
                         const float x = v[q] + sm.bias[L][c0 + q];
                         v[q] = fmaxf(x, x * p.slope);
+                    }
+                    if (SAVE) {   // this layer's activations: C1 / C2 / C3 region of the tile
+                        uint4* gact = grow + (L == 0 ? CSAVE_C1 : (L == 1 ? CSAVE_C2 : CSAVE_C3)) * SJ;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) gact[(c0 / 8 + q) * SJ] = pack8(v + 8 * q);
                     }
                     if (L < 2) {
 #pragma unroll
@@ -883,7 +903,8 @@ namespace pnerf {
 // pass (training); with `color` the tensor-core colour network follows (inference).
 int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack, const pnerf_mode* mode,
                     const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S, int SR, int K,
-                    float* sigma, float* rgb, void* F, uint8_t* save, float* save_w, float* save_raw, bool color, cudaStream_t st) {
+                    float* sigma, float* rgb, void* F, uint8_t* save, float* save_w, float* save_raw, bool color, uint8_t* csave,
+                    cudaStream_t st) {
     const int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
     FieldParams p;
     p.xyz = pts->xyz; p.embed = pts->embed; p.color = pts->color; p.dir = pts->dir; p.conf = pts->conf;
@@ -916,12 +937,17 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     c.wpack_c = (const uint8_t*)wpack + WPACK_FIELD_BYTES;
     c.bc1 = mlp->bc1; c.bc2 = mlp->bc2; c.bc3 = mlp->bc3; c.wc4 = mlp->wc4; c.bc4 = mlp->bc4;
     c.cam = p.cam; c.S = S; c.SR = SR; c.n_tiles = (S + ROWS - 1) / ROWS;
-    c.slope = mode->lrelu_slope; c.rgb = rgb;
+    c.slope = mode->lrelu_slope; c.rgb = rgb; c.csave = csave;
     const int c_super = (c.n_tiles + 1) / 2;
     const int cgrid = 2 * (c_super < kSMs / 2 ? c_super : kSMs / 2);   // CTA pairs
     const size_t csmem = sizeof(SmemC);
-    PNERF_CUDA(cudaFuncSetAttribute(color_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-    color_tc_kernel<<<cgrid, 288, csmem, st>>>(c);
+    if (csave) {
+        PNERF_CUDA(cudaFuncSetAttribute(color_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        color_tc_kernel<true><<<cgrid, 288, csmem, st>>>(c);
+    } else {
+        PNERF_CUDA(cudaFuncSetAttribute(color_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+        color_tc_kernel<false><<<cgrid, 288, csmem, st>>>(c);
+    }
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }
@@ -936,5 +962,5 @@ extern "C" int pnerf_field_forward_tc(const pnerf_points* pts, const pnerf_camer
     if (!workspace || workspace_bytes < pnerf_field_tc_workspace_bytes(S)) return PNERF_ERR_WORKSPACE;
     if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;   // lrelu(x) = max(x, slope x)
     return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, SR, K, sigma, rgb, workspace, nullptr,
-                           nullptr, nullptr, true, (cudaStream_t)stream);
+                           nullptr, nullptr, true, nullptr, (cudaStream_t)stream);
 }

@@ -12,7 +12,8 @@
 //                            tile, accumulated over a CTA's tiles in TMEM (128 x 288 fp32), fp32 red.add into dW at the end
 //   colsum_kernel    (SIMT)  d b_L = column sums of delta_L
 //   scatter_kernel   (SIMT)  d embed (raw + through the positional encoding), d color, d dir, d conf -> atomics by point id
-// The colour network runs in fp32 SIMT (field_f32.cu): 1/26 of the per-neighbour FLOPs.
+// The colour network (mlp_color + rgb head) takes the same route on 128-sample tiles kept by color_tc_kernel<SAVE>: color_head_bwd_kernel
+// (SIMT) -> tile_gemm_kernel x3 (K = 128) -> the same wgrad / colsum launches (job tables).
 #include "pnerf_common.cuh"
 #include "tc_layout.cuh"
 #include "umma.cuh"
@@ -24,7 +25,9 @@ using namespace tcl;
 
 constexpr int HID = 256;
 constexpr int NX0 = 224;                       // columns of the layer-1 input that carry a gradient: feat 32 + PE(feat) 192
-constexpr int64_t WB4 = 0, WB3 = 131072, WB2 = 262144, WB1 = 393216, WBWD_BYTES = 393216 + 32 * NX0 * 16;
+constexpr int HC = 128;
+constexpr int64_t WB4 = 0, WB3 = 131072, WB2 = 262144, WB1 = 393216, WBC3 = WB1 + 32 * NX0 * 16, WBC2 = WBC3 + 16 * HC * 16,
+                  WBC1 = WBC2 + 16 * HC * 16, WBWD_BYTES = WBC1 + 16 * HID * 16;
 
 struct Cam { float o[3]; float Rc[9]; float Rw[9]; };
 Cam make_cam(const pnerf_points* pts, const pnerf_camera* cam) {
@@ -52,11 +55,11 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 
 // ---------------------------------------------------------------------------------------------- transposed weight pack
 // Bt[k/8][n][8] with Bt(n, k) = W[k][n]: k = output feature of the forward layer (256), n = input feature (first `n_cols`).
-struct PackT { const float* w; int in_dim, n_cols; int64_t off; };
-struct PackTs { PackT j[4]; };
+struct PackT { const float* w; int in_dim, n_cols; int64_t off; int out_dim; };
+struct PackTs { PackT j[7]; };
 __global__ void __launch_bounds__(256) pack_bwd_kernel(PackTs jobs, uint8_t* __restrict__ dst) {
     const PackT jb = jobs.j[blockIdx.y];
-    const int total = HID * jb.n_cols;
+    const int total = jb.out_dim * jb.n_cols;
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst + jb.off);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int n = i % jb.n_cols, k = i / jb.n_cols;
@@ -132,11 +135,11 @@ __global__ void __launch_bounds__(128) agg_bwd_kernel(const AggBwd p) {
 
 // ---------------------------------------------------------------------------------------------- dgrad tile GEMM
 struct GemmP {
-    const uint8_t* in; int64_t in_stride;            // 128 x 256 bf16 operand tiles (K-major k-slabs), 64 KB each
+    const uint8_t* in; int64_t in_stride;            // 128 x K bf16 operand tiles (K-major k-slabs), K = 8 * ks (256 or 128)
     const uint8_t* mask; int64_t mask_stride;        // tiles whose sign gives lrelu' (same layout), or NULL
     uint8_t* out_bf; int64_t out_stride;             // bf16 tile output, or
     float* out_f32; int ld_f32;                      // fp32 row-major output (row = tile * 128 + r)
-    const uint8_t* w; int N; int n_tiles; float slope;
+    const uint8_t* w; int N; int ks; int n_tiles; float slope;
 };
 struct GemmSmem {
     uint8_t W[32 * HID * 16];
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256, 1) tile_gemm_kernel(const GemmP p) {
     const int N = p.N;
     if (warp == 0) {
         if (lane == 0 && n_my > 0) {
-            const uint32_t wbytes = (uint32_t)(32 * N * 16);
+            const uint32_t wbytes = (uint32_t)(p.ks * N * 16), abytes = (uint32_t)(p.ks * SLAB);
             mbar_arrive_expect_tx(&sm.w_bar, wbytes);
             for (int q = 0; q < 4; q++) bulk_g2s(sm.W + q * (wbytes / 4), p.w + q * (wbytes / 4), wbytes / 4, &sm.w_bar);
             mbar_wait(&sm.w_bar, 0);
@@ -172,12 +175,12 @@ __global__ void __launch_bounds__(256, 1) tile_gemm_kernel(const GemmP p) {
             for (int i = 0; i < n_my; i++) {
                 const int tile = (int)blockIdx.x + i * (int)gridDim.x, b = i & 1;
                 if (i > 0) mbar_wait(&sm.a_free, (uint32_t)((i - 1) & 1));
-                mbar_arrive_expect_tx(&sm.a_full, (uint32_t)DELTA_TILE_BYTES);
-                bulk_g2s(sm.A, p.in + (int64_t)tile * p.in_stride, (uint32_t)DELTA_TILE_BYTES, &sm.a_full);
+                mbar_arrive_expect_tx(&sm.a_full, abytes);
+                bulk_g2s(sm.A, p.in + (int64_t)tile * p.in_stride, abytes, &sm.a_full);
                 mbar_wait(&sm.a_full, (uint32_t)(i & 1));
                 if (i >= 2) mbar_wait(&sm.acc_empty[b], (uint32_t)(((i >> 1) - 1) & 1));
                 tc_fence_after();
-                for (int ks = 0; ks < HID / 16; ks++) {
+                for (int ks = 0; ks < p.ks / 2; ks++) {
                     const uint64_t ad = make_smem_desc(a_base + (uint32_t)(ks * 2 * SLAB), SLAB, 128);
                     const uint64_t bd = make_smem_desc(w_base + (uint32_t)(ks * 2 * N * 16), (uint32_t)(N * 16), 128);
                     mma_bf16(tmem + (uint32_t)(b * HID), ad, bd, idesc, (uint32_t)(ks > 0));
@@ -229,13 +232,14 @@ __global__ void __launch_bounds__(256, 1) tile_gemm_kernel(const GemmP p) {
 }
 
 // ---------------------------------------------------------------------------------------------- wgrad
-struct WgradP {
-    const uint8_t* d[4];            // delta_1 .. delta_4 tiles
-    const uint8_t* save;
-    float* dW[4];                   // (256, in_dim) fp32, accumulated into
-    int in_dim[4], xoff[4], xslabs[4];
+struct WgJob {
+    const uint8_t* d; int64_t d_stride; int d_slab0;          // gradient tiles: base, tile stride, first k-slab of this job's 128 output features
+    const uint8_t* x; int64_t x_stride; int x_slab0, xslabs;  // the layer's input tiles
+    float* dW; int in_dim, out0;                              // (out, in_dim) fp32, accumulated into; first output feature of the job
     int n_tiles;
 };
+constexpr int WG_MAX_JOBS = 12;
+struct WgradP { WgJob j[WG_MAX_JOBS]; int n_jobs; };
 struct WgSmem {
     uint8_t D[2][16 * SLAB];        // one 128-column half of a delta tile: M = 128 output features, K = 128 rows
     uint8_t X[2][36 * SLAB];        // the layer's input tile: N = up to 288 input features, K = 128 rows
@@ -247,10 +251,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int job = (int)blockIdx.x & 7, L = job >> 1, h = job & 1;
-    const int part = (int)blockIdx.x >> 3, parts = (int)gridDim.x >> 3;
-    const int n_my = p.n_tiles > part ? (p.n_tiles - part + parts - 1) / parts : 0;
-    const int xslabs = p.xslabs[L];
+    const WgJob& jb = p.j[(int)blockIdx.x % p.n_jobs];
+    const int part = (int)blockIdx.x / p.n_jobs, parts = (int)gridDim.x / p.n_jobs;
+    const int n_my = jb.n_tiles > part ? (jb.n_tiles - part + parts - 1) / parts : 0;
+    const int xslabs = jb.xslabs;
     if (tid == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
         mbar_init(&sm.done, 1);
@@ -268,14 +272,14 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
                 if (i >= 2) mbar_wait(&sm.empty[s], (uint32_t)(((i >> 1) - 1) & 1));
                 const uint32_t xbytes = (uint32_t)(xslabs * SLAB);
                 mbar_arrive_expect_tx(&sm.full[s], 16u * SLAB + xbytes);
-                bulk_g2s(sm.D[s], p.d[L] + (int64_t)tile * DELTA_TILE_BYTES + (int64_t)h * 16 * SLAB, 16u * SLAB, &sm.full[s]);
-                bulk_g2s(sm.X[s], p.save + (int64_t)tile * SAVE_TILE_BYTES + (int64_t)p.xoff[L] * SLAB, xbytes, &sm.full[s]);
+                bulk_g2s(sm.D[s], jb.d + (int64_t)tile * jb.d_stride + (int64_t)jb.d_slab0 * SLAB, 16u * SLAB, &sm.full[s]);
+                bulk_g2s(sm.X[s], jb.x + (int64_t)tile * jb.x_stride + (int64_t)jb.x_slab0 * SLAB, xbytes, &sm.full[s]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && n_my > 0) {   // MMA issuer: both operands MN-major (k = tile rows): LBO = 128 (next 8 rows), SBO = SLAB (next 8 features)
             const uint32_t mn = (1u << 15) | (1u << 16);
-            const uint32_t idesc_main = make_idesc_bf16(ROWS, 256) | mn, idesc_tail = make_idesc_bf16(ROWS, 32) | mn;
+            const uint32_t idesc_main = make_idesc_bf16(ROWS, xslabs >= 32 ? 256 : xslabs * 8) | mn, idesc_tail = make_idesc_bf16(ROWS, 32) | mn;
             for (int i = 0; i < n_my; i++) {
                 const int s = i & 1;
                 mbar_wait(&sm.full[s], (uint32_t)((i >> 1) & 1));
@@ -297,10 +301,10 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
     } else if (warp >= 4 && n_my > 0) {
         mbar_wait(&sm.done, 0);
         tc_fence_after();
-        const int o = h * 128 + (warp & 3) * 32 + lane;          // output feature = accumulator lane
+        const int o = jb.out0 + (warp & 3) * 32 + lane;          // output feature = accumulator lane
         const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        float* dst = p.dW[L] + (int64_t)o * p.in_dim[L];
-        const int in_dim = p.in_dim[L];
+        float* dst = jb.dW + (int64_t)o * jb.in_dim;
+        const int in_dim = jb.in_dim;
 #pragma unroll 1
         for (int c0 = 0; c0 < xslabs * 8; c0 += 32) {
             float v[32];
@@ -318,29 +322,91 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
 
 // ---------------------------------------------------------------------------------------------- bias gradients
 // db_L[c] = sum over rows of delta_L[r][c].  Thread = (slab, 16-row group); block = one tile at a time.
-struct ColsumP { const uint8_t* d[4]; float* db[4]; int n_tiles; };
+struct ColsumJob { const uint8_t* d; int64_t d_stride; int n_slabs; float* db; int n_tiles; };
+struct ColsumP { ColsumJob j[7]; };
 __global__ void __launch_bounds__(256) colsum_kernel(const ColsumP p) {
     __shared__ float s_part[8][HID];
-    const int L = blockIdx.y, t = threadIdx.x;
+    const ColsumJob jb = p.j[blockIdx.y];
+    const int t = threadIdx.x;
     const int slab = t >> 3, rg = t & 7;
     float acc[8] = {};
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.d[L] + (int64_t)tile * DELTA_TILE_BYTES + (int64_t)slab * SLAB) + rg * 16;
+    if (slab < jb.n_slabs) {
+        for (int tile = blockIdx.x; tile < jb.n_tiles; tile += gridDim.x) {
+            const uint4* src = reinterpret_cast<const uint4*>(jb.d + (int64_t)tile * jb.d_stride + (int64_t)slab * SLAB) + rg * 16;
 #pragma unroll 4
-        for (int r = 0; r < 16; r++) {
-            float f[8];
-            unpack8(__ldg(src + r), f);
+            for (int r = 0; r < 16; r++) {
+                float f[8];
+                unpack8(__ldg(src + r), f);
 #pragma unroll
-            for (int e = 0; e < 8; e++) acc[e] += f[e];
+                for (int e = 0; e < 8; e++) acc[e] += f[e];
+            }
         }
     }
 #pragma unroll
     for (int e = 0; e < 8; e++) s_part[rg][slab * 8 + e] = acc[e];
     __syncthreads();
-    float s = 0.f;
+    float sum = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; g++) s += s_part[g][t];
-    if (p.db[L]) atomicAdd(p.db[L] + t, s);
+    for (int g = 0; g < 8; g++) sum += s_part[g][t];
+    if (jb.db && t < jb.n_slabs * 8) atomicAdd(jb.db + t, sum);
+}
+
+// ---------------------------------------------------------------------------------------------- rgb head backward
+// rgb = sigmoid(Wc4 c3 + bc4) * 1.002 - 0.001 (SM:358-359): d raw, delta_c3 = lrelu'(c3) * (Wc4^T d raw) per sample; d Wc4, d bc4.
+struct HeadBwd {
+    const uint8_t* csave; const int* sample_ids; const float *d_rgb, *rgb, *wc4;
+    int S, n_tiles; float slope;
+    uint8_t* d3; float *dwc4, *dbc4;
+};
+__global__ void __launch_bounds__(128) color_head_bwd_kernel(const HeadBwd p) {
+    __shared__ float s_w4[3][HC];
+    __shared__ float s_dz[3][ROWS];
+    const int row = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 3; j++) s_w4[j][row] = p.wc4[j * HC + row];
+    float gw[3] = {0.f, 0.f, 0.f}, gb = 0.f;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        __syncthreads();
+        const int si = tile * ROWS + row;
+        float dz[3] = {0.f, 0.f, 0.f};
+        if (si < p.S) {
+            const int slot = p.sample_ids[si];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const float sg = (p.rgb[3 * (int64_t)slot + j] + 0.001f) * (1.f / 1.002f);
+                dz[j] = p.d_rgb[3 * (int64_t)slot + j] * 1.002f * sg * (1.f - sg);
+            }
+        }
+        const uint4* c3 = reinterpret_cast<const uint4*>(p.csave + (int64_t)tile * CSAVE_TILE_BYTES + (int64_t)CSAVE_C3 * SLAB + row * 16);
+        uint4* out = reinterpret_cast<uint4*>(p.d3 + (int64_t)tile * CDELTA_TILE_BYTES + row * 16);
+#pragma unroll 4
+        for (int j = 0; j < HC / 8; j++) {
+            float h[8], g[8];
+            unpack8(c3[j * (SLAB / 16)], h);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int c = 8 * j + e;
+                g[e] = (dz[0] * s_w4[0][c] + dz[1] * s_w4[1][c] + dz[2] * s_w4[2][c]) * (h[e] > 0.f ? 1.f : p.slope);
+            }
+            out[j * (SLAB / 16)] = pack8(g);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; j++) s_dz[j][row] = dz[j];
+        __syncthreads();
+        // d Wc4[j][c] += sum_rows dz_j c3[row][c]: thread t owns column t
+        const __nv_bfloat16* col = reinterpret_cast<const __nv_bfloat16*>(p.csave + (int64_t)tile * CSAVE_TILE_BYTES + (int64_t)CSAVE_C3 * SLAB) +
+                                   (row >> 3) * (SLAB / 2) + (row & 7);
+        for (int r = 0; r < ROWS; r++) {
+            const float h = __bfloat162float(col[r * 8]);
+            gw[0] = fmaf(s_dz[0][r], h, gw[0]); gw[1] = fmaf(s_dz[1][r], h, gw[1]); gw[2] = fmaf(s_dz[2][r], h, gw[2]);
+            if (row < 3) gb += s_dz[row][r];
+        }
+    }
+    if (p.dwc4) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) atomicAdd(p.dwc4 + j * HC + row, gw[j]);
+        if (row < 3 && p.dbc4) atomicAdd(p.dbc4 + row, gb);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------- scatter to the points
@@ -432,8 +498,9 @@ __global__ void __launch_bounds__(128) scatter_kernel(const ScatterP p) {
 }
 
 struct TrainWs {
-    uint8_t* F; uint8_t* save; float *save_w, *save_raw; float* color; uint8_t* d[4]; float* dx0; float* dw_rows; uint8_t* wbwd;
-    int64_t total;
+    uint8_t* F; uint8_t* save; float *save_w, *save_raw; uint8_t* csave; uint8_t* d[4]; uint8_t* dc[3]; float* dF; float* dx0; float* dw_rows;
+    uint8_t* wbwd;
+    int64_t n_tiles, n_ctiles, total;
 };
 TrainWs carve_train(void* base, int64_t S, int K) {
     const int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
@@ -446,7 +513,12 @@ TrainWs carve_train(void* base, int64_t S, int K) {
     w.save = take(n_tiles * SAVE_TILE_BYTES);
     w.save_w = (float*)take(rows * 4);
     w.save_raw = (float*)take(rows * 4);
-    w.color = (float*)take(color_f32_ws_floats(S) * 4);
+    // colour tiles of 128 samples (the colour kernel works on CTA pairs too: even count)
+    const int64_t n_ctiles = ((S + ROWS - 1) / ROWS + 1) / 2 * 2;
+    w.n_tiles = n_tiles; w.n_ctiles = n_ctiles;
+    w.csave = take(n_ctiles * CSAVE_TILE_BYTES);
+    for (int i = 0; i < 3; i++) w.dc[i] = take(n_ctiles * CDELTA_TILE_BYTES);
+    w.dF = (float*)take(n_ctiles * ROWS * HID * 4);
     for (int i = 0; i < 4; i++) w.d[i] = take(n_tiles * DELTA_TILE_BYTES);
     w.dx0 = (float*)take(rows * NX0 * 4);
     w.dw_rows = (float*)take(rows * 4);
@@ -469,20 +541,17 @@ extern "C" int pnerf_field_forward_tc_train(const pnerf_points* pts, const pnerf
     if (S == 0) return PNERF_OK;
     if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < pnerf_field_tc_train_workspace_bytes(S, K)) return PNERF_ERR_WORKSPACE;
     if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
     TrainWs w = carve_train(workspace, S, K);
-    int rc = field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, SR, K, sigma, rgb, w.F, w.save, w.save_w,
-                             w.save_raw, false, st);
-    if (rc) return rc;
-    return color_forward_f32(pts, cam, mlp, mode, dirs, sample_ids, S, SR, w.F, w.color, rgb, st);
+    return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, SR, K, sigma, rgb, w.F, w.save, w.save_w,
+                           w.save_raw, true, w.csave, (cudaStream_t)stream);
 }
 
 extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const pnerf_mode* mode,
                                        const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S,
-                                       int SR, int K, const float* d_sigma, const float* d_rgb, float* g_embed, float* g_color,
-                                       float* g_dir, float* g_conf, const pnerf_mlp_grad* gm, void* workspace, int64_t workspace_bytes,
-                                       void* stream) {
-    if (!pts || !cam || !mlp || !mode || !gm || S < 0 || K <= 0 || K > 32 || SR <= 0 || !d_sigma || !d_rgb) return PNERF_ERR_ARG;
+                                       int SR, int K, const float* d_sigma, const float* d_rgb, const float* rgb, float* g_embed,
+                                       float* g_color, float* g_dir, float* g_conf, const pnerf_mlp_grad* gm, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+    if (!pts || !cam || !mlp || !mode || !gm || S < 0 || K <= 0 || K > 32 || SR <= 0 || !d_sigma || !d_rgb || !rgb) return PNERF_ERR_ARG;
     if (S == 0) return PNERF_OK;
     if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < pnerf_field_tc_train_workspace_bytes(S, K)) return PNERF_ERR_WORKSPACE;
     (void)sample_loc;
@@ -490,60 +559,83 @@ extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_came
     TrainWs w = carve_train(workspace, S, K);
     const int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
     const int n_tiles = (int)((S + ROWS / KP - 1) / (ROWS / KP));
-    // colour network (fp32) -> dF_s
-    const float* dF; int ldF;
-    int rc = color_backward_f32(mlp, gm, mode, sample_ids, S, d_rgb, w.color, &dF, &ldF, st);
-    if (rc) return rc;
-    // transposed bf16 weights of the four 256-wide layers
+    const int n_ctiles = (int)((S + ROWS - 1) / ROWS);
+    const float slope = mode->lrelu_slope;
+    // transposed bf16 weights: Bt(n = input feature, k = output feature)
     PackTs jobs;
-    jobs.j[0] = {mlp->w4, 256, 256, WB4}; jobs.j[1] = {mlp->w3, 263, 256, WB3}; jobs.j[2] = {mlp->w2, 256, 256, WB2}; jobs.j[3] = {mlp->w1, 284, NX0, WB1};
-    pack_bwd_kernel<<<dim3(64, 4), 256, 0, st>>>(jobs, w.wbwd);
+    jobs.j[0] = {mlp->w4, 256, 256, WB4, 256}; jobs.j[1] = {mlp->w3, 263, 256, WB3, 256}; jobs.j[2] = {mlp->w2, 256, 256, WB2, 256};
+    jobs.j[3] = {mlp->w1, 284, NX0, WB1, 256};
+    jobs.j[4] = {mlp->wc3, 128, 128, WBC3, 128}; jobs.j[5] = {mlp->wc2, 128, 128, WBC2, 128}; jobs.j[6] = {mlp->wc1, 280, 256, WBC1, 128};
+    pack_bwd_kernel<<<dim3(64, 7), 256, 0, st>>>(jobs, w.wbwd);
     PNERF_LAUNCH_CHECK();
-    // aggregation + density head backward -> delta_4
+    const size_t gsm = sizeof(GemmSmem);
+    PNERF_CUDA(cudaFuncSetAttribute(tile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
+    auto gemm = [&](const uint8_t* in, int64_t in_stride, int ks, const uint8_t* mask, int64_t mask_stride, uint8_t* out_bf,
+                    int64_t out_stride, float* out_f32, int ld, int64_t wb, int N, int tiles) -> int {
+        GemmP g;
+        g.in = in; g.in_stride = in_stride; g.ks = ks; g.mask = mask; g.mask_stride = mask_stride;
+        g.out_bf = out_bf; g.out_stride = out_stride; g.out_f32 = out_f32; g.ld_f32 = ld;
+        g.w = w.wbwd + wb; g.N = N; g.n_tiles = tiles; g.slope = slope;
+        tile_gemm_kernel<<<tiles < kSMs ? tiles : kSMs, 256, gsm, st>>>(g);
+        PNERF_LAUNCH_CHECK();
+        return PNERF_OK;
+    };
+    int rc;
+    // ---- colour network: rgb head -> delta_c3 -> delta_c2 -> delta_c1 -> dF_s
+    HeadBwd hb;
+    hb.csave = w.csave; hb.sample_ids = sample_ids; hb.d_rgb = d_rgb; hb.rgb = rgb; hb.wc4 = mlp->wc4; hb.S = S; hb.n_tiles = n_ctiles;
+    hb.slope = slope; hb.d3 = w.dc[2]; hb.dwc4 = gm->wc4; hb.dbc4 = gm->bc4;
+    color_head_bwd_kernel<<<n_ctiles < kSMs * 8 ? n_ctiles : kSMs * 8, 128, 0, st>>>(hb);
+    PNERF_LAUNCH_CHECK();
+    if ((rc = gemm(w.dc[2], CDELTA_TILE_BYTES, 16, w.csave + (int64_t)CSAVE_C2 * SLAB, CSAVE_TILE_BYTES, w.dc[1], CDELTA_TILE_BYTES, nullptr, 0,
+                   WBC3, 128, n_ctiles))) return rc;                                   // delta_c2 = lrelu'(c2) * (delta_c3 Wc3)
+    if ((rc = gemm(w.dc[1], CDELTA_TILE_BYTES, 16, w.csave + (int64_t)CSAVE_C1 * SLAB, CSAVE_TILE_BYTES, w.dc[0], CDELTA_TILE_BYTES, nullptr, 0,
+                   WBC2, 128, n_ctiles))) return rc;                                   // delta_c1 = lrelu'(c1) * (delta_c2 Wc2)
+    if ((rc = gemm(w.dc[0], CDELTA_TILE_BYTES, 16, nullptr, 0, nullptr, 0, w.dF, HID, WBC1, 256, n_ctiles))) return rc;   // dF_s = delta_c1 Wc1[:, :256]
+    // ---- aggregation + density head backward -> delta_4
     AggBwd a;
-    a.save = w.save; a.save_w = w.save_w; a.save_raw = w.save_raw; a.sample_ids = sample_ids; a.d_sigma = d_sigma; a.dF = dF; a.ldF = ldF;
-    a.wa = mlp->wa; a.S = S; a.KP = KP; a.n_tiles = n_tiles; a.softplus = mode->density_softplus; a.slope = mode->lrelu_slope;
+    a.save = w.save; a.save_w = w.save_w; a.save_raw = w.save_raw; a.sample_ids = sample_ids; a.d_sigma = d_sigma; a.dF = w.dF; a.ldF = HID;
+    a.wa = mlp->wa; a.S = S; a.KP = KP; a.n_tiles = n_tiles; a.softplus = mode->density_softplus; a.slope = slope;
     a.d4 = w.d[3]; a.dwa = gm->wa; a.dba = gm->ba; a.dw_rows = w.dw_rows;
     agg_bwd_kernel<<<n_tiles < kSMs * 8 ? n_tiles : kSMs * 8, 128, 0, st>>>(a);
     PNERF_LAUNCH_CHECK();
-    // dgrad chain
-    const size_t gsm = sizeof(GemmSmem);
-    PNERF_CUDA(cudaFuncSetAttribute(tile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
-    const int ggrid = n_tiles < kSMs ? n_tiles : kSMs;
+    // ---- dgrad chain of mlp_head / mlp_base
     auto dgrad = [&](const uint8_t* in, int mask_slab, uint8_t* out_bf, float* out_f32, int64_t wb, int N) -> int {
-        GemmP g;
-        g.in = in; g.in_stride = DELTA_TILE_BYTES;
-        g.mask = mask_slab >= 0 ? w.save + (int64_t)mask_slab * SLAB : nullptr; g.mask_stride = SAVE_TILE_BYTES;
-        g.out_bf = out_bf; g.out_stride = DELTA_TILE_BYTES; g.out_f32 = out_f32; g.ld_f32 = NX0;
-        g.w = w.wbwd + wb; g.N = N; g.n_tiles = n_tiles; g.slope = mode->lrelu_slope;
-        tile_gemm_kernel<<<ggrid, 256, gsm, st>>>(g);
-        PNERF_LAUNCH_CHECK();
-        return PNERF_OK;
+        return gemm(in, DELTA_TILE_BYTES, 32, mask_slab >= 0 ? w.save + (int64_t)mask_slab * SLAB : nullptr, SAVE_TILE_BYTES, out_bf,
+                    DELTA_TILE_BYTES, out_f32, NX0, wb, N, n_tiles);
     };
     if ((rc = dgrad(w.d[3], SAVE_H3, w.d[2], nullptr, WB4, 256))) return rc;      // delta_3 = lrelu'(h3) * (delta_4 W4)
     if ((rc = dgrad(w.d[2], SAVE_X3, w.d[1], nullptr, WB3, 256))) return rc;      // delta_2 = lrelu'(h2) * (delta_3 W3[:, :256])
     if ((rc = dgrad(w.d[1], SAVE_H1, w.d[0], nullptr, WB2, 256))) return rc;      // delta_1 = lrelu'(h1) * (delta_2 W2)
     if (g_embed && (rc = dgrad(w.d[0], -1, nullptr, w.dx0, WB1, NX0))) return rc; // d x0[:, :224] = delta_1 W1[:, :224]
-    // wgrad + bias gradients
-    if (gm->w1 && gm->w2 && gm->w3 && gm->w4) {
+    // ---- wgrad + bias gradients: one launch each for all seven layers
+    {
         WgradP g;
-        for (int i = 0; i < 4; i++) g.d[i] = w.d[i];
-        g.save = w.save; g.n_tiles = n_tiles;
-        g.dW[0] = gm->w1; g.dW[1] = gm->w2; g.dW[2] = gm->w3; g.dW[3] = gm->w4;
-        g.in_dim[0] = 284; g.in_dim[1] = 256; g.in_dim[2] = 263; g.in_dim[3] = 256;
-        g.xoff[0] = SAVE_X0; g.xoff[1] = SAVE_H1; g.xoff[2] = SAVE_X3; g.xoff[3] = SAVE_H3;
-        g.xslabs[0] = 36; g.xslabs[1] = 32; g.xslabs[2] = 36; g.xslabs[3] = 32;
-        const size_t wsm = sizeof(WgSmem);
-        PNERF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
-        wgrad_tc_kernel<<<8 * (kSMs / 8), 256, wsm, st>>>(g);
-        PNERF_LAUNCH_CHECK();
+        int nj = 0;
+        float* dWf[4] = {gm->w1, gm->w2, gm->w3, gm->w4};
+        const int in_dim[4] = {284, 256, 263, 256}, xoff[4] = {SAVE_X0, SAVE_H1, SAVE_X3, SAVE_H3}, xsl[4] = {36, 32, 36, 32};
+        for (int L = 0; L < 4; L++)
+            for (int h = 0; h < 2; h++)
+                if (dWf[L]) g.j[nj++] = {w.d[L], DELTA_TILE_BYTES, 16 * h, w.save, SAVE_TILE_BYTES, xoff[L], xsl[L], dWf[L], in_dim[L], 128 * h, n_tiles};
+        float* dWc[3] = {gm->wc1, gm->wc2, gm->wc3};
+        const int cin[3] = {280, 128, 128}, coff[3] = {CSAVE_C0, CSAVE_C1, CSAVE_C2}, csl[3] = {36, 16, 16};
+        for (int L = 0; L < 3; L++)
+            if (dWc[L]) g.j[nj++] = {w.dc[L], CDELTA_TILE_BYTES, 0, w.csave, CSAVE_TILE_BYTES, coff[L], csl[L], dWc[L], cin[L], 0, n_ctiles};
+        g.n_jobs = nj;
+        if (nj > 0) {
+            const size_t wsm = sizeof(WgSmem);
+            PNERF_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsm));
+            wgrad_tc_kernel<<<nj * (kSMs / nj), 256, wsm, st>>>(g);
+            PNERF_LAUNCH_CHECK();
+        }
         ColsumP c;
-        for (int i = 0; i < 4; i++) c.d[i] = w.d[i];
-        c.db[0] = gm->b1; c.db[1] = gm->b2; c.db[2] = gm->b3; c.db[3] = gm->b4; c.n_tiles = n_tiles;
-        colsum_kernel<<<dim3(n_tiles < 64 ? n_tiles : 64, 4), 256, 0, st>>>(c);
+        float* db[7] = {gm->b1, gm->b2, gm->b3, gm->b4, gm->bc1, gm->bc2, gm->bc3};
+        for (int i = 0; i < 4; i++) c.j[i] = {w.d[i], DELTA_TILE_BYTES, 32, db[i], n_tiles};
+        for (int i = 0; i < 3; i++) c.j[4 + i] = {w.dc[i], CDELTA_TILE_BYTES, 16, db[4 + i], n_ctiles};
+        colsum_kernel<<<dim3(n_tiles < 64 ? n_tiles : 64, 7), 256, 0, st>>>(c);
         PNERF_LAUNCH_CHECK();
     }
-    // point gradients
+    // ---- point gradients
     if (g_embed || g_color || g_dir || (g_conf && mode->weight_conf)) {
         ScatterP s;
         s.cam = make_cam(pts, cam);

@@ -15,18 +15,15 @@ constexpr int SLAB = ROWS * 16;                  // bytes of one 8-wide k-slab o
 constexpr int SAVE_X0 = 0, SAVE_H1 = 36, SAVE_X3 = 68, SAVE_H3 = 104, SAVE_H4 = 136, SAVE_SLABS = 168;
 constexpr int64_t SAVE_TILE_BYTES = (int64_t)SAVE_SLABS * SLAB;     // 344 064
 constexpr int64_t DELTA_TILE_BYTES = (int64_t)32 * SLAB;            // a 128 x 256 bf16 gradient tile
+// colour network operands kept per 128-sample tile: [C0 = [F_s | PE(v) | 0] 36 slabs | C1 16 | C2 16 | C3 16]
+constexpr int CSAVE_C0 = 0, CSAVE_C1 = 36, CSAVE_C2 = 52, CSAVE_C3 = 68, CSAVE_SLABS = 84;
+constexpr int64_t CSAVE_TILE_BYTES = (int64_t)CSAVE_SLABS * SLAB;   // 172 032
+constexpr int64_t CDELTA_TILE_BYTES = (int64_t)16 * SLAB;           // a 128 x 128 bf16 gradient tile
 }  // namespace tcl
 
 int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack, const pnerf_mode* mode,
                     const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S, int SR, int K,
-                    float* sigma, float* rgb, void* F, uint8_t* save, float* save_w, float* save_raw, bool color, cudaStream_t st);
+                    float* sigma, float* rgb, void* F, uint8_t* save, float* save_w, float* save_raw, bool color, uint8_t* csave,
+                    cudaStream_t st);
 
-// fp32 colour network (mlp_color + rgb head) on an (S,256) bf16 feature matrix: used by the tensor-core training path, implemented
-// with the SIMT kernels of field_f32.cu.  `ws` holds color_f32_ws_floats(S) floats and carries the activations to the backward.
-int64_t color_f32_ws_floats(int64_t S);
-int color_forward_f32(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const pnerf_mode* mode, const float* dirs,
-                      const int* sample_ids, int S, int SR, const void* F_bf16, float* ws, float* rgb, cudaStream_t st);
-// -> *dF = (S, ldF) fp32 gradient of the aggregated features (inside ws)
-int color_backward_f32(const pnerf_mlp* mlp, const pnerf_mlp_grad* gm, const pnerf_mode* mode, const int* sample_ids, int S,
-                       const float* d_rgb, float* ws, const float** dF, int* ldF, cudaStream_t st);
 }  // namespace pnerf

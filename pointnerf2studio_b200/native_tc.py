@@ -116,7 +116,7 @@ class _RenderTC(torch.autograd.Function):
         gm = make_mlp(grads, _lib.MlpGrad)
         with Timers.span("field_bwd"):
             check(lib.pnerf_field_backward_tc(C.byref(pts), C.byref(cam), C.byref(mlp), C.byref(mode), _ptr(dirs), _ptr(q.sample_loc),
-                                              _ptr(q.sample_pidx), _ptr(ids), S, SR, K, _ptr(d_sigma), _ptr(d_rgb), _ptr(g_embed),
+                                              _ptr(q.sample_pidx), _ptr(ids), S, SR, K, _ptr(d_sigma), _ptr(d_rgb), _ptr(rgb), _ptr(g_embed),
                                               _ptr(g_color), _ptr(g_dir), _ptr(g_conf), C.byref(gm), _ptr(ws), ws.numel(), _stream()),
                   "pnerf_field_backward_tc")
         LAUNCHES["n"] += 22
