@@ -232,16 +232,26 @@ class NeuralPoints(nn.Module):
         ranges_tensor = torch.as_tensor(np.concatenate([f.lo, f.hi]), device=point_xyz_w_tensor.device)
         return ranges_tensor, vsize_np, f.dim
 
+    _CAM_CACHE = {}
+
     @staticmethod
     def camera_of(ray_bundle, with_near_far=False):
         """SU:148-155: one camera per call; rotation and origin come from ray 0 (and near / far, SU:154-155).
         One device->host transfer for all of them."""
         rot = ray_bundle.metadata["camrotc2w"]
         rot = rot[0].view(3, 3) if rot.shape[0] != 3 else rot
-        parts = [ray_bundle.origins[0].detach().float().reshape(-1), rot.detach().float().reshape(-1)]
-        if with_near_far:
-            parts += [ray_bundle.nears[0].detach().float().reshape(-1)[:1], ray_bundle.fars[0].detach().float().reshape(-1)[:1]]
-        h = torch.cat(parts).cpu().numpy()
+        # the same device tensors again (a bundle rendered / trained on repeatedly): reuse the host copy, no device->host sync
+        key = (ray_bundle.origins.data_ptr(), ray_bundle.origins._version, rot.data_ptr(), rot._version, with_near_far,
+               ray_bundle.nears.data_ptr() if with_near_far else 0, ray_bundle.fars.data_ptr() if with_near_far else 0)
+        hit = NeuralPoints._CAM_CACHE.get("k")
+        if hit == key:
+            h = NeuralPoints._CAM_CACHE["v"]
+        else:
+            parts = [ray_bundle.origins[0].detach().float().reshape(-1), rot.detach().float().reshape(-1)]
+            if with_near_far:
+                parts += [ray_bundle.nears[0].detach().float().reshape(-1)[:1], ray_bundle.fars[0].detach().float().reshape(-1)[:1]]
+            h = torch.cat(parts).cpu().numpy()
+            NeuralPoints._CAM_CACHE["k"], NeuralPoints._CAM_CACHE["v"] = key, h
         if with_near_far:
             return h[:3].copy(), h[3:12].reshape(3, 3).copy(), float(h[12]), float(h[13])
         return h[:3].copy(), h[3:12].reshape(3, 3).copy()
