@@ -4,28 +4,32 @@
 // (twin PA:486-662,745-830); the reference runs the same math as ~40 separate torch/cuBLAS launches with every
 // (M,256) fp32 activation round-tripping HBM.
 //
-// field_tc_kernel -- CTA PAIRS (cluster of 2 = the two SMs of a TPC, tcgen05 cta_group::2), one CTA per SM, 448 threads,
+// field_tc_kernel -- CTA PAIRS (cluster of 2 = the two SMs of a TPC, tcgen05 cta_group::2), one CTA per SM, 704 threads,
 // two tile slots in ping-pong.  One MMA (M = 256, N = 256, K = 16) spans the pair: each CTA supplies its own 128 rows
-// of A and only HALF of every weight chunk (its 128 of the 256 output features), so the L2 -> SM weight stream -- the
-// bound of the single-CTA version (557 KB per 128-row tile against ~43 B/clk/SM of L2) -- is halved per SM.
+// of A and only HALF of every weight chunk (its 128 of the 256 output features), so the L2 -> SM weight stream is halved per SM.
 //   tile      = 128 rows = (128/KP) consecutive valid samples x KP neighbour slots (KP = 8, 16 or 32 >= K)
-//   warps 0-7 : encoder, two threads per row (each half of the embedding; dists / weights+extras): gathers the point (xyz, 32-d embedding, colour, dir, conf), computes the
-//               relative position in world and perspective space, the inverse-distance weight, the 284-wide encoded
-//               input (double-angle recurrences from one sincos per input) and writes it as the bf16 A operand of
-//               layer 1 straight into shared memory (K-slab layout, see umma.cuh).  Nothing encoded touches HBM.
-//   warps 8-15 / 16-23 : epilogue group of slot 0 / 1, two warps per 32 TMEM lanes (one per 128-column half: the roles
-//               are latency-bound, so a second warp per lane quarter nearly halves an epilogue).  Thread = row = TMEM
-//               lane: tcgen05.ld the fp32 accumulator, bias + LeakyReLU, bf16 pack, write the next layer's A operand in
-//               place; after layer 4 the density head (in-thread dot, halves combined through shared memory), the
-//               weight w_k and the sum over the KP neighbour lanes (register butterfly).
-//   warp 24   : weight producer: streams this CTA's half of the four 256-wide layers (bf16, pre-packed K-slabs, L2
-//               resident) as 8 KB half-chunks through an 8-stage ring with cp.async.bulk + mbarrier complete_tx.
-//   warp 25   : leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 for slot 0 / slot 1 alternately,
-//               so one slot's epilogue overlaps the other slot's MMAs; multicast tcgen05.commit releases ring stages
-//               and publishes accumulators in both CTAs.  Peer CTA: relay -- forwards "my half-chunk has landed" to
-//               the leader.  Barriers the issuer waits on live in the leader (remote arrivals from the peer).
+//   warps 0-3 : encoder (thread = row; ENC_PARTS = 2 splits a row over two threads): neighbour / sample ids are loaded two
+//               tiles ahead and the point rows prefetched into L2; gathers the point (xyz, 32-d embedding, colour, dir, conf),
+//               computes the relative position in world and perspective space, the inverse-distance weight, the 284-wide
+//               encoded input (double-angle recurrences from one sincos per input) plus the constant-1 column that carries
+//               the bias, and writes it as the bf16 A operand of layer 1 straight into shared memory (K-slab layout, see
+//               umma.cuh).  Nothing encoded touches HBM (except SAVE mode, which keeps every operand tile for the backward).
+//   warps 4-11 / 12-19 : epilogue group of slot 0 / 1, two warps per 32 TMEM lanes (one per 128-column half).  Thread = row =
+//               TMEM lane: tcgen05.ld the fp32 accumulator (the next 32 columns are requested before the current 32 are
+//               processed), LeakyReLU, bf16 pack, write the next layer's A operand in place; after layer 4 the density head
+//               (in-thread dot, halves combined through shared memory), the weight w_k and the sum over the KP neighbour
+//               lanes (register butterfly); the accumulator is released right after its last load.
+//   warp 20   : weight producer: two issuing lanes stream this CTA's half of the four 256-wide layers (bf16, pre-packed
+//               K-slabs with the bias column, L2 resident) as 12 KB half-chunks, three groups of two chunks in flight,
+//               cp.async.bulk + mbarrier complete_tx.
+//   warp 21   : leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 for the two slots, slot 1 one layer
+//               behind slot 0, so one slot's epilogue (and its tile boundary) overlaps the other slot's MMAs; ONE multicast
+//               tcgen05.commit per weight group releases the ring stage, one per layer publishes the accumulator in both CTAs.
+//               Peer CTA: relay -- forwards "my half of the group has landed" to the leader.  Barriers the issuer waits on live
+//               in the leader (remote arrivals from the peer); every wait is an mbarrier.try_wait with a suspend-time hint.
 //   TMEM      : 512 columns = 2 slots x (128 lanes x 256 fp32 columns).
 //   HBM       : in 168 B per valid row (gather) + indices; out 4 B sigma + 512 B F_s (bf16) per sample.
+// Measured design choices (tools/tc_microbench.py, tools/tc_trace.py, tools/sweep_field_tc.sh) are listed in DESIGN.md section 4.
 #include "pnerf_common.cuh"
 #include "tc_layout.cuh"
 #include "umma.cuh"
@@ -107,7 +111,7 @@ struct FieldParams {
     const float *dirs, *sample_loc;
     const int *sample_pidx, *sample_ids;
     const uint8_t* wpack;
-    const float *b1, *b2, *b3, *b4, *wa, *ba;
+    const float *wa, *ba;                    // density head (the four layer biases ride in the packed weights)
     Cam cam;
     int S, SR, K, n_tiles;
     float slope;
@@ -910,7 +914,7 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     p.xyz = pts->xyz; p.embed = pts->embed; p.color = pts->color; p.dir = pts->dir; p.conf = pts->conf;
     p.dirs = dirs; p.sample_loc = sample_loc; p.sample_pidx = sample_pidx; p.sample_ids = sample_ids;
     p.wpack = (const uint8_t*)wpack;
-    p.b1 = mlp->b1; p.b2 = mlp->b2; p.b3 = mlp->b3; p.b4 = mlp->b4; p.wa = mlp->wa; p.ba = mlp->ba;
+    p.wa = mlp->wa; p.ba = mlp->ba;
     p.cam = make_cam(pts, cam);
     p.S = S; p.SR = SR; p.K = K;
     const int spt = ROWS / KP;
