@@ -294,13 +294,47 @@ __device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int 
 }
 
 // ---------------------------------------------------------------------------------------------- epilogues
+// The kernel is co-bound by warp-instruction issue (ncu: 29 k warp-instructions per tile against 11 k tensor-pipe clocks), and
+// 40 % of those were the FMUL / FMNMX of LeakyReLU.  Blackwell's packed fp32 arithmetic (mul / fma / add .f32x2: two IEEE fp32
+// results per instruction, bit-identical to the scalar forms) halves the multiplies and adds of the epilogues.
+#ifndef PNERF_F32X2
+#define PNERF_F32X2 1
+#endif
+__device__ __forceinline__ uint64_t pack2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ void mul2(float& a, float& b, float s) {            // (a, b) *= s
+#if PNERF_F32X2
+    uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a, b)), "l"(pack2(s, s))); unpack2(r, a, b);
+#else
+    a *= s; b *= s;
+#endif
+}
+__device__ __forceinline__ void add2(float& a, float& b, float c, float d) {   // (a, b) += (c, d)
+#if PNERF_F32X2
+    uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(a, b)), "l"(pack2(c, d))); unpack2(r, a, b);
+#else
+    a += c; b += d;
+#endif
+}
+__device__ __forceinline__ void fma2(float& a, float& b, float x, float y, float u, float v) {   // (a, b) += (x * u, y * v)
+#if PNERF_F32X2
+    uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(x, y)), "l"(pack2(u, v)), "l"(pack2(a, b))); unpack2(r, a, b);
+#else
+    a = fmaf(x, u, a); b = fmaf(y, v, b);
+#endif
+}
+__device__ __forceinline__ void lrelu2(float& a, float& b, float slope) {      // LeakyReLU = max(x, slope * x), 0 < slope < 1
+    float sa = a, sb = b;
+    mul2(sa, sb, slope);
+    a = fmaxf(a, sa); b = fmaxf(b, sb);
+}
 // Hidden-layer epilogue of one 128-column half: bias + LeakyReLU in fp32, bf16 pack, next layer's A operand in place.
 // tcgen05.ld takes ~210 clk while the tensor pipe works on the other slot (60 clk idle; tools/tc_microbench.py), so the load
 // of chunk i+1 is issued before chunk i is processed (tcgen05.wait::ld waits for every outstanding load, hence the order).
 template <bool SAVE>
 __device__ __forceinline__ void epilogue_chunk_store(float (&v)[32], float slope, const RowSink<SAVE>& A, int c0) {
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], v[j] * slope);       // the bias is already in the accumulator
+    for (int j = 0; j < 32; j += 2) lrelu2(v[j], v[j + 1], slope);       // the bias is already in the accumulator
 #pragma unroll
     for (int j = 0; j < 4; j++) A.put(c0 / 8 + j, pack8(v + 8 * j));
 }
@@ -327,11 +361,17 @@ __device__ __forceinline__ void epilogue_store(uint32_t tacc_lane, float slope, 
 template <int D, int N>
 __device__ __forceinline__ void bfly_step(float* a, int lane) {
     const bool up = (lane & D) != 0;
+    if constexpr (N == 2) {
+        const float send = up ? a[0] : a[1], keep = up ? a[1] : a[0];
+        a[0] = keep + __shfl_xor_sync(0xffffffffu, send, D);
+    } else {
 #pragma unroll
-    for (int j = 0; j < N / 2; j++) {
-        const float send = up ? a[j] : a[j + N / 2];
-        const float keep = up ? a[j + N / 2] : a[j];
-        a[j] = keep + __shfl_xor_sync(0xffffffffu, send, D);
+        for (int j = 0; j + 1 < N / 2; j += 2) {
+            const float s0 = up ? a[j] : a[j + N / 2], s1 = up ? a[j + 1] : a[j + 1 + N / 2];
+            float k0 = up ? a[j + N / 2] : a[j], k1 = up ? a[j + 1 + N / 2] : a[j + 1];
+            add2(k0, k1, __shfl_xor_sync(0xffffffffu, s0, D), __shfl_xor_sync(0xffffffffu, s1, D));
+            a[j] = k0; a[j + 1] = k1;
+        }
     }
 }
 template <int KP>
@@ -344,25 +384,24 @@ __device__ __forceinline__ void butterfly(float* a, int lane) {
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
 template <int KP, bool SAVE>
-__device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)[32], const float* __restrict__ wa, float w, float& dot,
+__device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)[32], const float* __restrict__ wa, float w, float& dot, float& dot1,
                                                 int slot, int si, int c0, int lane, uint4* gh4) {
     constexpr int VPL = 32 / KP;
     const int gl = lane % KP;
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(wa + c0 + j));
-        float x;
-        x = v[j]; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.x, dot); v[j] = x;
-        x = v[j + 1]; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.y, dot); v[j + 1] = x;
-        x = v[j + 2]; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.z, dot); v[j + 2] = x;
-        x = v[j + 3]; x = fmaxf(x, x * p.slope); dot = fmaf(x, a.w, dot); v[j + 3] = x;
+        lrelu2(v[j], v[j + 1], p.slope);
+        lrelu2(v[j + 2], v[j + 3], p.slope);
+        fma2(dot, dot1, v[j], v[j + 1], a.x, a.y);
+        fma2(dot, dot1, v[j + 2], v[j + 3], a.z, a.w);
     }
     if (SAVE) {
 #pragma unroll
         for (int j = 0; j < 4; j++) gh4[(c0 / 8 + j) * (SLAB / 16)] = pack8(v + 8 * j);
     }
 #pragma unroll
-    for (int j = 0; j < 32; j++) v[j] *= w;
+    for (int j = 0; j < 32; j += 2) mul2(v[j], v[j + 1], w);
     butterfly<KP>(v, lane);
     if (slot >= 0) {
         __nv_bfloat16* dst = p.F + (int64_t)si * HID + c0 + gl * VPL;
@@ -387,20 +426,20 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
     const int si = tile * SPT + sl;
     const float w = meta.w[row];
     const int slot = meta.slot_id[sl];
-    float dot = 0.f;
+    float dot = 0.f, dot1 = 0.f;     // even / odd columns of the density head
 #pragma unroll 1
     for (int cbeg = (EPW == 8 ? half * (HID / 2) : 0); cbeg < (EPW == 8 ? (half + 1) * (HID / 2) : HID); cbeg += HID / 2) {
         float va[32], vb[32];
         tmem_ld32(tacc_lane + cbeg, va);
         tmem_ld_wait();
         tmem_ld32(tacc_lane + cbeg + 32, vb);
-        aggregate_chunk<KP, SAVE>(p, va, wa, w, dot, slot, si, cbeg, lane, gh4);
+        aggregate_chunk<KP, SAVE>(p, va, wa, w, dot, dot1, slot, si, cbeg, lane, gh4);
         tmem_ld_wait();
         tmem_ld32(tacc_lane + cbeg + 64, va);
-        aggregate_chunk<KP, SAVE>(p, vb, wa, w, dot, slot, si, cbeg + 32, lane, gh4);
+        aggregate_chunk<KP, SAVE>(p, vb, wa, w, dot, dot1, slot, si, cbeg + 32, lane, gh4);
         tmem_ld_wait();
         tmem_ld32(tacc_lane + cbeg + 96, vb);
-        aggregate_chunk<KP, SAVE>(p, va, wa, w, dot, slot, si, cbeg + 64, lane, gh4);
+        aggregate_chunk<KP, SAVE>(p, va, wa, w, dot, dot1, slot, si, cbeg + 64, lane, gh4);
         tmem_ld_wait();
         if (cbeg + HID / 2 >= (EPW == 8 ? (half + 1) * (HID / 2) : HID)) {
             // this warp's last TMEM load has landed: the accumulator may be overwritten by the slot's next tile while the last
@@ -409,8 +448,9 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(acc_empty, 0);
         }
-        aggregate_chunk<KP, SAVE>(p, vb, wa, w, dot, slot, si, cbeg + 96, lane, gh4);
+        aggregate_chunk<KP, SAVE>(p, vb, wa, w, dot, dot1, slot, si, cbeg + 96, lane, gh4);
     }
+    dot += dot1;
     // combine the two column halves of the density head: the upper-half warp hands its partial dot to the lower-half warp
     float dot_other = 0.f;
     if (EPW == 8) {
