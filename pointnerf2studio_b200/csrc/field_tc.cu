@@ -476,16 +476,41 @@ __host__ __device__ constexpr int chunk_slabs(int L, int c) {
 }
 
 // The order in which (slot, layer) steps go through the tensor pipe, shared by the weight producer, the MMA issuer and the
-// relay.  Slot s works on this CTA's tiles j = 2*it + s; step q of a slot is layer q & 3 of its tile q >> 2.  Slot 1 runs
-// two layers behind slot 0, so the encoder has two layer-times of the other slot's MMAs to refill a slot's A buffer.
+// relay (the issue order is static because the weight stream has to be prefetched in that order).  Slot s works on this CTA's
+// tiles j = 2*it + s; step q of a slot is layer q & 3 of its tile q >> 2.
+// What the order has to hide (pipeline trace, clocks): a layer's MMAs T = 2.85 k, a hidden-layer epilogue E = 1.3 k, a tile
+// boundary B = 6.5 k (aggregation epilogue drains the accumulator while the ONE encoder group writes the slot's next tile).
+// Strict alternation s0 s1 s0 s1 ... puts one layer of the other slot between a slot's L3 and its next L0 and makes both
+// boundaries coincide: the pipe idles B - T per boundary and the second encode queues behind the first (7.9 k of 33.2 k clk per
+// pair of tiles).  PNERF_ORDER 1 runs the slots two layers apart in the period
+//      s0L0 s1L2 s0L1 s1L3 s0L2 s0L3 s1L0' s1L1'
+// so that TWO layers of the other slot (+ its epilogue gap) lie inside every boundary and the two encodes never overlap; the
+// price is one exposed epilogue E per slot and period (s0L2->s0L3, s1L0->s1L1).
+#ifndef PNERF_ORDER
+#define PNERF_ORDER 1
+#endif
 template <class F>
 __device__ __forceinline__ void for_each_step(int n_my, F&& fn) {
     const int n0 = 4 * ((n_my + 1) >> 1), n1 = 4 * (n_my >> 1);
+#if PNERF_ORDER == 1
+    auto go = [&](int s, int q) { if (q >= 0 && q < (s ? n1 : n0)) fn(s, q & 3, q >> 2); };
+    for (int k = 0; 4 * k < n0 + 4; k++) {
+        go(0, 4 * k);
+        go(1, 4 * k - 2);
+        go(0, 4 * k + 1);
+        go(1, 4 * k - 1);
+        go(0, 4 * k + 2);
+        go(0, 4 * k + 3);
+        go(1, 4 * k);
+        go(1, 4 * k + 1);
+    }
+#else
     const int n = n0 > n1 + STAGGER ? n0 : n1 + STAGGER;
     for (int a = 0; a < n; a++) {
         if (a >= STAGGER && a - STAGGER < n1) fn(1, (a - STAGGER) & 3, (a - STAGGER) >> 2);
         if (a < n0) fn(0, a & 3, a >> 2);
     }
+#endif
 }
 
 template <int KP, bool SAVE>
