@@ -117,7 +117,7 @@ struct FieldParams {
     float slope;
     int softplus, weight_conf;
     float* sigma;                   // (R*SR) by slot
-    __nv_bfloat16* F;               // (S, 256) aggregated features, by compact sample index
+    uint8_t* F;                     // aggregated features by compact sample index, 128-sample tiles of 32 k-slabs (tc_layout.cuh)
     unsigned long long* trace;      // profiling hook (pnerf_tc_set_trace): per-warp event timelines of CTA 0, or NULL
     // training: every MMA operand of the forward pass is kept for the backward GEMMs, in the tile layout it had in shared
     // memory (so a backward kernel bulk-copies it straight back into an operand buffer):
@@ -404,14 +404,15 @@ __device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)
     for (int j = 0; j < 32; j += 2) mul2(v[j], v[j + 1], w);
     butterfly<KP>(v, lane);
     if (slot >= 0) {
-        __nv_bfloat16* dst = p.F + (int64_t)si * HID + c0 + gl * VPL;
+        const int c = c0 + gl * VPL;
+        uint8_t* dst = p.F + (int64_t)(si / ROWS) * F_TILE_BYTES + (c >> 3) * SLAB + (si % ROWS) * 16 + (c & 7) * 2;
         if (VPL == 4) {
             uint2 o; o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
             *reinterpret_cast<uint2*>(dst) = o;
         } else if (VPL == 2) {
             *reinterpret_cast<uint32_t*>(dst) = pack_bf16(v[0], v[1]);
         } else {
-            dst[0] = __float2bfloat16(v[0]);
+            *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16(v[0]);
         }
     }
 }
@@ -707,7 +708,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
 // is free): one slot's gather and epilogues hide under the other's MMAs.  v1 (one slot, 128 threads, everything serial per tile) ran
 // at 12.6 % tensor-pipe activity, 18 k clk per tile.
 struct ColorParams {
-    const __nv_bfloat16* F;
+    const uint8_t* F;              // 128-sample tiles of 32 k-slabs, written by field_tc_kernel
     const int* sample_ids;
     const float* dirs;
     const uint8_t* wpack_c;        // Wc1 | Wc2 | Wc3, each as two N-halves of k-slabs [k/8][64][8]
@@ -727,7 +728,7 @@ struct SmemC {
     uint8_t W3[C2H_BYTES];
     float bias[3][HC];
     float w4[3][HC];
-    uint64_t bar_w, a_ready[2], acc_full[2];
+    uint64_t bar_w, a_ready[2], acc_full[2], f_full[2];
     uint32_t tmem_base;
 };
 static_assert(sizeof(SmemC) <= 232448, "color_tc_kernel shared memory exceeds the 227 KB per-CTA limit");
@@ -752,7 +753,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
     const int n_my = n_super > pair ? (n_super - pair + n_pairs - 1) / n_pairs : 0;
     if (tid == 0) {
         mbar_init(&sm.bar_w, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&sm.a_ready[s], 8); mbar_init(&sm.acc_full[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&sm.a_ready[s], 8); mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.f_full[s], 1); }
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc2(&sm.tmem_base, 256);
@@ -777,21 +778,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
         const int s = warp >> 2, row = tid & 127;
         const uint32_t tacc_lane = tmem + (uint32_t)(s * HC) + ((uint32_t)((warp & 3) * 32) << 16);
         uint4* Arow = reinterpret_cast<uint4*>(sm.A[s] + row * 16);
-        uint32_t ph = 0;
+        uint32_t ph = 0, fph = 0;
         bool w_ready = false;
+        // the F part of the A operand (slabs 0..31 = 64 KB, contiguous in global memory) arrives by bulk copy; the copy for the slot's
+        // next tile is issued as soon as the last layer's MMAs have released the buffer
+        auto tile_of = [&](int j) { return 2 * (pair + j * n_pairs) + (int)rank; };
+        auto fetch = [&](int j) {
+            const int ct = tile_of(j);
+            if (ct * ROWS >= p.S) return;
+            mbar_arrive_expect_tx(&sm.f_full[s], (uint32_t)F_TILE_BYTES);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                bulk_g2s(sm.A[s] + q * (F_TILE_BYTES / 4), p.F + (int64_t)ct * F_TILE_BYTES + q * (F_TILE_BYTES / 4), (uint32_t)(F_TILE_BYTES / 4),
+                         &sm.f_full[s]);
+        };
+        if (row == 0 && s < n_my) fetch(s);
         for (int j = s; j < n_my; j += 2) {
-            const int ctile = 2 * (pair + j * n_pairs) + (int)rank;
+            const int ctile = tile_of(j);
             const int si = ctile * ROWS + row;
             uint4* grow = SAVE ? reinterpret_cast<uint4*>(p.csave + (int64_t)ctile * CSAVE_TILE_BYTES + row * 16) : nullptr;
             int slot = -1;
+            if (ctile * ROWS < p.S) { mbar_wait(&sm.f_full[s], fph); fph ^= 1; }
             if (si < p.S) {
                 slot = __ldg(p.sample_ids + si);
-                const uint4* f4 = reinterpret_cast<const uint4*>(p.F + (int64_t)si * HID);
+                if (SAVE) {
 #pragma unroll 8
-                for (int q = 0; q < 32; q++) {
-                    const uint4 fv = __ldg(f4 + q);
-                    Arow[q * SJ] = fv;
-                    if (SAVE) grow[q * SJ] = fv;
+                    for (int q = 0; q < 32; q++) grow[q * SJ] = Arow[q * SJ];
                 }
                 const int ray = slot / p.SR;
                 const float rd[3] = {__ldg(p.dirs + 3 * (int64_t)ray), __ldg(p.dirs + 3 * (int64_t)ray + 1), __ldg(p.dirs + 3 * (int64_t)ray + 2)};
@@ -830,6 +842,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
             for (int L = 0; L < 3; L++) {
                 mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
                 tc_fence_after();
+                if (L == 2 && row == 0 && j + 2 < n_my) fetch(j + 2);     // the tile's last MMAs are done with the A buffer
                 float r[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
                 for (int c0 = 0; c0 < HC; c0 += 32) {
@@ -965,7 +978,9 @@ extern "C" int pnerf_tc_pack_weights(const pnerf_mlp* mlp, void* wpack, void* st
     return PNERF_OK;
 }
 
-extern "C" int64_t pnerf_field_tc_workspace_bytes(int64_t n_samples) { return align_up(n_samples * HID * 2, 256) + 256; }
+extern "C" int64_t pnerf_field_tc_workspace_bytes(int64_t n_samples) {
+    return ((n_samples + ROWS - 1) / ROWS + 1) / 2 * 2 * F_TILE_BYTES + 256;      // whole 128-sample tiles, an even number of them (CTA pairs)
+}
 
 namespace pnerf {
 // Fused per-neighbour networks (sigma by slot + F (S,256) bf16); with `save` != NULL every MMA operand is kept for the backward
@@ -985,7 +1000,7 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     const int spt = ROWS / KP;
     p.n_tiles = (S + spt - 1) / spt;
     p.slope = mode->lrelu_slope; p.softplus = mode->density_softplus; p.weight_conf = mode->weight_conf;
-    p.sigma = sigma; p.F = (__nv_bfloat16*)F; p.trace = g_trace;
+    p.sigma = sigma; p.F = (uint8_t*)F; p.trace = g_trace;
     p.save = save; p.save_w = save_w; p.save_raw = save_raw;
     const int n_super = (p.n_tiles + 1) / 2;
     const int grid = 2 * (n_super < kSMs / 2 ? n_super : kSMs / 2);   // CTA pairs
@@ -996,10 +1011,25 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
         PNERF_LAUNCH_CHECK();
         return PNERF_OK;
     };
+#ifdef PNERF_TC_TIMING      // debug build (tools/sweep_field_tc.sh "-DPNERF_TC_TIMING"): in-stream time of the two kernels of the previous call
+    static cudaEvent_t g_tev[3]; static bool tev_init = false; static float tacc[2] = {0.f, 0.f}; static int n_calls = 0;
+    if (!tev_init) { for (auto& e : g_tev) cudaEventCreate(&e); tev_init = true; }
+    else if (color) {
+        cudaEventSynchronize(g_tev[2]);
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, g_tev[0], g_tev[1]); cudaEventElapsedTime(&b, g_tev[1], g_tev[2]);
+        tacc[0] += a; tacc[1] += b;
+        if (++n_calls % 7 == 0) { fprintf(stderr, "[tc timing] field %.3f ms colour %.3f ms per 7 calls\n", tacc[0], tacc[1]); tacc[0] = tacc[1] = 0.f; }
+    }
+    cudaEventRecord(g_tev[0], st);
+#endif
     int rc;
     if (save) rc = KP == 8 ? launch(field_tc_kernel<8, true>) : (KP == 16 ? launch(field_tc_kernel<16, true>) : launch(field_tc_kernel<32, true>));
     else rc = KP == 8 ? launch(field_tc_kernel<8, false>) : (KP == 16 ? launch(field_tc_kernel<16, false>) : launch(field_tc_kernel<32, false>));
     if (rc || !color) return rc;
+#ifdef PNERF_TC_TIMING
+    cudaEventRecord(g_tev[1], st);
+#endif
 
     ColorParams c;
     c.F = p.F; c.sample_ids = sample_ids; c.dirs = dirs;
@@ -1018,6 +1048,9 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
         color_tc_kernel<false><<<cgrid, 288, csmem, st>>>(c);
     }
     PNERF_LAUNCH_CHECK();
+#ifdef PNERF_TC_TIMING
+    cudaEventRecord(g_tev[2], st);
+#endif
     return PNERF_OK;
 }
 }  // namespace pnerf

@@ -509,7 +509,7 @@ TrainWs carve_train(void* base, int64_t S, int K) {
     uint8_t* p = (uint8_t*)base;
     TrainWs w;
     auto take = [&](int64_t bytes) { uint8_t* r = p; p += align_up(bytes, 1024); return r; };
-    w.F = take(S * HID * 2);
+    w.F = take(((S + ROWS - 1) / ROWS + 1) / 2 * 2 * F_TILE_BYTES);
     w.save = take(n_tiles * SAVE_TILE_BYTES);
     w.save_w = (float*)take(rows * 4);
     w.save_raw = (float*)take(rows * 4);

@@ -19,6 +19,9 @@ constexpr int64_t DELTA_TILE_BYTES = (int64_t)32 * SLAB;            // a 128 x 2
 constexpr int CSAVE_C0 = 0, CSAVE_C1 = 36, CSAVE_C2 = 52, CSAVE_C3 = 68, CSAVE_SLABS = 84;
 constexpr int64_t CSAVE_TILE_BYTES = (int64_t)CSAVE_SLABS * SLAB;   // 172 032
 constexpr int64_t CDELTA_TILE_BYTES = (int64_t)16 * SLAB;           // a 128 x 128 bf16 gradient tile
+// aggregated features F between the two forward kernels: per 128-sample tile 32 k-slabs = the first 32 slabs of the colour network's
+// A operand, so the colour kernel fetches a tile with bulk copies instead of a per-thread gather
+constexpr int64_t F_TILE_BYTES = (int64_t)32 * SLAB;                // 65 536
 }  // namespace tcl
 
 int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack, const pnerf_mode* mode,
