@@ -141,7 +141,9 @@ def host_bundle(cam, pix, pinned=True):
 
 def to_device(ts, RayBundle):
     o, d, n, f, rot = [t.cuda(non_blocking=True) for t in ts]
-    return RayBundle(origins=o, directions=d, nears=n, fars=f, metadata={"camrotc2w": rot})
+    # the host still holds the camera: tell the model, so that it does not read ray 0 back from the device (a host sync per call)
+    host_cam = {"origin": ts[0][0].numpy(), "camrotc2w": ts[4].numpy(), "near": float(ts[2][0, 0]), "far": float(ts[3][0, 0])}
+    return RayBundle(origins=o, directions=d, nears=n, fars=f, metadata={"camrotc2w": rot, "camera_host": host_cam})
 
 
 def timed_steps(step_fn, K, flush, dist):

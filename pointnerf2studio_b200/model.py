@@ -238,6 +238,13 @@ class NeuralPoints(nn.Module):
     def camera_of(ray_bundle, with_near_far=False):
         """SU:148-155: one camera per call; rotation and origin come from ray 0 (and near / far, SU:154-155).
         One device->host transfer for all of them."""
+        hint = ray_bundle.metadata.get("camera_host")
+        if hint is not None and (not with_near_far or ("near" in hint and "far" in hint)):
+            # a caller that still has the camera on the host (a server that just uploaded the rays) says so: no device->host
+            # read-back, hence no host sync between the upload and the first kernel launch
+            o = np.asarray(hint["origin"], dtype=np.float32).reshape(3).copy()
+            r = np.asarray(hint["camrotc2w"], dtype=np.float32).reshape(3, 3).copy()
+            return (o, r, float(hint["near"]), float(hint["far"])) if with_near_far else (o, r)
         rot = ray_bundle.metadata["camrotc2w"]
         rot = rot[0].view(3, 3) if rot.shape[0] != 3 else rot
         # the same device tensors again (a bundle rendered / trained on repeatedly): reuse the host copy, no device->host sync

@@ -277,6 +277,22 @@ def test_eval_mode_clamps_and_chunks():
     assert float(a["coarse_raycolor"].min()) >= 0 and float(a["coarse_raycolor"].max()) <= 1
 
 
+def test_camera_host_hint_equals_device_readback():
+    """metadata["camera_host"] (origin / rotation / near / far still on the caller's host) replaces the read-back of ray 0."""
+    from pointnerf2studio_b200 import RayBundle
+    s, cloud, cam, pix = _scene("tinyP")
+    model = _make_model(cloud, "fp32", "plugin", SR=16, K=4, P=3)
+    model.eval()
+    rb = _bundle(cam, pix)
+    hint = {"origin": np.asarray(cam.origin, np.float32), "camrotc2w": np.asarray(cam.R_c2w, np.float32), "near": cam.near, "far": cam.far}
+    rb_hint = RayBundle(origins=rb.origins.clone(), directions=rb.directions.clone(), nears=rb.nears.clone(), fars=rb.fars.clone(),
+                        metadata={"camrotc2w": rb.metadata["camrotc2w"].clone(), "camera_host": hint})
+    a = model.get_outputs_for_camera_ray_bundle(rb)
+    b = model.get_outputs_for_camera_ray_bundle(rb_hint)
+    torch.testing.assert_close(a["coarse_raycolor"], b["coarse_raycolor"], rtol=0, atol=0)
+    assert torch.equal(a["ray_mask"], b["ray_mask"])
+
+
 def test_in_kernel_jitter_replays_through_t_table():
     """The jittered selection generates its t mid-points in registers (Philox); pnerf_coarse_t exposes the same table.
     (a) the table follows RM:312-329 evaluated in float64 on the same uniforms, (b) the uniforms are uniform and differ
