@@ -14,6 +14,7 @@ from ._lib import check
 from .native import LAUNCHES, MLP_PARAM_NAMES, Timers, _ptr, _stream, make_mlp, make_points
 
 _PACK_CACHE = {}
+MAX_SAMPLES_PER_LAUNCH = 1 << 23      # valid samples per field-kernel launch (4.3 GB of bf16 features); a memory knob only
 
 
 def packed_weights(mlp_params):
@@ -40,13 +41,18 @@ def field_forward_tc(cfg, q, dirs, pts, mlp, wpack, ids, S: int):
     dev = dirs.device
     sigma = torch.zeros((R, SR), dtype=torch.float32, device=dev)
     rgb = torch.zeros((R, SR, 3), dtype=torch.float32, device=dev)
-    ws_bytes = lib.pnerf_field_tc_workspace_bytes(S)
+    # the aggregated features between the two kernels cost 512 B per valid sample: the compact sample list is walked in pieces so
+    # that a dense scene (up to R * SR samples) cannot ask for more than MAX_SAMPLES_PER_LAUNCH * 512 B of workspace
+    piece = min(S, MAX_SAMPLES_PER_LAUNCH)
+    ws_bytes = lib.pnerf_field_tc_workspace_bytes(piece)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
     with Timers.span("field"):
-        check(lib.pnerf_field_forward_tc(C.byref(pts), C.byref(cfg["camera"]), C.byref(mlp), _ptr(wpack), C.byref(cfg["mode"]),
-                                         _ptr(dirs), _ptr(q.sample_loc), _ptr(q.sample_pidx), _ptr(ids), S, SR, K, _ptr(sigma),
-                                         _ptr(rgb), _ptr(ws), ws_bytes, _stream()), "pnerf_field_forward_tc")
-    LAUNCHES["n"] += 2
+        for off in range(0, S, max(piece, 1)):
+            n = min(piece, S - off)
+            check(lib.pnerf_field_forward_tc(C.byref(pts), C.byref(cfg["camera"]), C.byref(mlp), _ptr(wpack), C.byref(cfg["mode"]),
+                                             _ptr(dirs), _ptr(q.sample_loc), _ptr(q.sample_pidx), ids.data_ptr() + 4 * off, n, SR, K,
+                                             _ptr(sigma), _ptr(rgb), _ptr(ws), ws_bytes, _stream()), "pnerf_field_forward_tc")
+            LAUNCHES["n"] += 2
     return sigma, rgb
 
 

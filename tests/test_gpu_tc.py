@@ -68,6 +68,24 @@ def test_tc_full_image_chunks_agree_with_fp32_kernels():
     assert float((ca - cb).abs().max()) <= 2e-2
 
 
+def test_tc_sample_pieces_are_bit_identical(monkeypatch):
+    """The compact sample list is walked in pieces of MAX_SAMPLES_PER_LAUNCH (a memory bound on the bf16 feature tiles between the
+    two kernels); samples are independent, so any piece size -- including ones that split a 128-sample tile -- gives the same bits."""
+    from pointnerf2studio_b200 import native_tc
+    s, cloud, cam, pix = _scene("config1")
+    W = of.FieldWeights.random(seed=4, scale=1.2)
+    m = _make_model(cloud, "bf16", "plugin", SR=s["SR"], K=s["K"], P=s["P"], weights=W).eval()
+    rb = _bundle(cam, pix)
+    with torch.no_grad():
+        whole = m.get_outputs(rb)["coarse_raycolor"].clone()
+        S = int(m.last_query_dense().sample_valid.sum().item())
+        assert S > 1000
+        for piece in (1000, 128, S - 1):
+            monkeypatch.setattr(native_tc, "MAX_SAMPLES_PER_LAUNCH", piece)
+            got = m.get_outputs(rb)["coarse_raycolor"]
+            assert torch.equal(got, whole), piece
+
+
 @pytest.mark.parametrize("flow,K", [("plugin", 8), ("original", 8), ("plugin", 16)])
 def test_tc_training_forward_backward_matches_fp32_autograd(flow, K):
     """Tensor-core training path (operands kept by the fused forward; bf16 tcgen05 dgrad / wgrad GEMMs) against torch autograd
