@@ -22,13 +22,15 @@
 //   warp 20   : weight producer: two issuing lanes stream this CTA's half of the four 256-wide layers (bf16, pre-packed
 //               K-slabs with the bias column, L2 resident) as 12 KB half-chunks, three groups of two chunks in flight,
 //               cp.async.bulk + mbarrier complete_tx.
-//   warp 21   : leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 for the two slots, slot 1 one layer
-//               behind slot 0, so one slot's epilogue (and its tile boundary) overlaps the other slot's MMAs; ONE multicast
+//   warp 21   : leader CTA: MMA issuer -- one thread issues tcgen05.mma.cta_group::2 for the two slots in the static 8-step
+//               period of for_each_step (slots two layers apart: two layers of the other slot lie inside every tile boundary),
+//               so one slot's epilogues and its tile boundary overlap the other slot's MMAs; ONE multicast
 //               tcgen05.commit per weight group releases the ring stage, one per layer publishes the accumulator in both CTAs.
 //               Peer CTA: relay -- forwards "my half of the group has landed" to the leader.  Barriers the issuer waits on live
 //               in the leader (remote arrivals from the peer); every wait is an mbarrier.try_wait with a suspend-time hint.
 //   TMEM      : 512 columns = 2 slots x (128 lanes x 256 fp32 columns).
-//   HBM       : in 168 B per valid row (gather) + indices; out 4 B sigma + 512 B F_s (bf16) per sample.
+//   HBM       : in 168 B per valid row (gather) + indices; out 4 B sigma + 512 B F_s (bf16, in the colour kernel's operand layout:
+//               128-sample tiles of 32 k-slabs, tc_layout.cuh) per sample.
 // Measured design choices (tools/tc_microbench.py, tools/tc_trace.py, tools/sweep_field_tc.sh) are listed in DESIGN.md section 4.
 #include "pnerf_common.cuh"
 #include "tc_layout.cuh"
@@ -60,10 +62,6 @@ constexpr int BIAS_COL[4] = {284, 256, 263, 256};
 // EPW 8 (832 threads, 72 registers, spills): 17.5 ms although a tile encodes in 4.5 k instead of 7.4 k clk; ENC_PARTS 2 / EPW 4:
 // 19.3 ms.  More warps do not shorten the epilogues -- the roles contend for issue slots in bursts -- so instructions, not
 // warps, are what the next version has to cut.
-#ifndef PNERF_STAGGER
-#define PNERF_STAGGER 1
-#endif
-constexpr int STAGGER = PNERF_STAGGER;           // layers by which slot 1 trails slot 0 (field kernels of the render bench: 0 -> 16.0 ms, 1 -> 14.3 ms, 2 -> 16.0 ms, 3 -> 15.8 ms)
 #ifndef PNERF_ENC_PARTS
 #define PNERF_ENC_PARTS 1
 #endif
@@ -483,17 +481,13 @@ __host__ __device__ constexpr int chunk_slabs(int L, int c) {
 // boundary B = 6.5 k (aggregation epilogue drains the accumulator while the ONE encoder group writes the slot's next tile).
 // Strict alternation s0 s1 s0 s1 ... puts one layer of the other slot between a slot's L3 and its next L0 and makes both
 // boundaries coincide: the pipe idles B - T per boundary and the second encode queues behind the first (7.9 k of 33.2 k clk per
-// pair of tiles).  PNERF_ORDER 1 runs the slots two layers apart in the period
+// pair of tiles; field kernels of the render bench 13.6 ms).  Instead the slots run two layers apart in the period
 //      s0L0 s1L2 s0L1 s1L3 s0L2 s0L3 s1L0' s1L1'
 // so that TWO layers of the other slot (+ its epilogue gap) lie inside every boundary and the two encodes never overlap; the
 // price is one exposed epilogue E per slot and period (s0L2->s0L3, s1L0->s1L1).
-#ifndef PNERF_ORDER
-#define PNERF_ORDER 1
-#endif
 template <class F>
 __device__ __forceinline__ void for_each_step(int n_my, F&& fn) {
     const int n0 = 4 * ((n_my + 1) >> 1), n1 = 4 * (n_my >> 1);
-#if PNERF_ORDER == 1
     auto go = [&](int s, int q) { if (q >= 0 && q < (s ? n1 : n0)) fn(s, q & 3, q >> 2); };
     for (int k = 0; 4 * k < n0 + 4; k++) {
         go(0, 4 * k);
@@ -505,13 +499,6 @@ __device__ __forceinline__ void for_each_step(int n_my, F&& fn) {
         go(1, 4 * k);
         go(1, 4 * k + 1);
     }
-#else
-    const int n = n0 > n1 + STAGGER ? n0 : n1 + STAGGER;
-    for (int a = 0; a < n; a++) {
-        if (a >= STAGGER && a - STAGGER < n1) fn(1, (a - STAGGER) & 3, (a - STAGGER) >> 2);
-        if (a < n0) fn(0, a & 3, a >> 2);
-    }
-#endif
 }
 
 template <int KP, bool SAVE>
