@@ -424,7 +424,7 @@ def main():
     # dram__bytes_read + dram__bytes_write of field_tc_kernel<8,0> for one launch of this very workload (ncu --set full,
     # profiles/r01_final_ncu_full.md): 0.58 GB read + 1.62 GB written, against 5.3 GB of algorithmic gather + output bytes
     # (neighbouring samples share points, the gathers hit L2).  Only quoted for the workload it was captured on.
-    traffic = 2.205e9 if (args.workload == "render" and args.points == N_POINTS and precision == "bf16") else None
+    traffic = 2.194e9 if (args.workload == "render" and args.points == N_POINTS and precision == "bf16") else None
     roofline = {"kernel": "field networks (gather + per-neighbour MLP + aggregation + colour MLP)", "bound": "tensor",
                 "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
                 "traffic_unit": "bytes of DRAM traffic per launch of field_tc_kernel (ncu, profiles/r01_final_ncu_full.md)",
