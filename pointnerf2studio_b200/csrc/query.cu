@@ -219,8 +219,13 @@ __device__ __forceinline__ void list_insert(float (&bd2)[KMAX], int (&bidx)[KMAX
 // for every lane (a rejected or missing candidate carries d2 = +inf and changes nothing).  The nested per-run loops this
 // replaces executed sum_runs max_lane(len) iterations with a divergent 48-instruction insertion: 979 M warp instructions
 // for the render bench.
+// K <= 8: 62 registers leave 8 blocks (32 warps) per SM; capping at 56 (9 blocks) costs no spills and hides more of the record
+// loads' latency: -11 % on the render bench (tools/sweep_query.sh on one box: 1.65 / 1.46 / 1.53 ms at 8 / 9 / 10 blocks)
+#ifndef PNERF_Q_MINB
+#define PNERF_Q_MINB 9
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(128) query_kernel(Frame f, const int* __restrict__ cell_start,
+__global__ void __launch_bounds__(128, KMAX <= 8 ? PNERF_Q_MINB : 1) query_kernel(Frame f, const int* __restrict__ cell_start,
                                                      const float4* __restrict__ recs, const float* __restrict__ sample_loc,
                                                      const int* __restrict__ sample_cnt, int R, int SR, int K, int layers,
                                                      float r2, int max_runs, int* __restrict__ sample_pidx,
