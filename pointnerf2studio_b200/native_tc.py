@@ -57,7 +57,7 @@ def field_forward_tc(cfg, q, dirs, pts, mlp, wpack, ids, S: int):
 
 
 class _RenderTC(torch.autograd.Function):
-    """Tensor-core training path: fused per-neighbour networks (operands kept), fp32 colour network, step length + compositing
+    """Tensor-core training path: fused per-neighbour networks and colour network (operand tiles kept), step length + compositing
     as one autograd node; backward = composite backward + bf16 tcgen05 dgrad / wgrad GEMMs + scatter into the point tensors."""
 
     @staticmethod
