@@ -239,6 +239,14 @@ int pnerf_probe(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pner
                 const uint8_t* sample_valid, const float* sigma, const int* sample_pidx, int R, int SR, int K, float* max_opacity,
                 float* max_loc, float* far_dist, float* avg_color, float* avg_dir, float* avg_conf, float* avg_embed, void* stream);
 
+/* Masked-ray MSE of get_loss_dict (studio_model.py:415-426): loss_out[0] = sum_{ray_mask > 0} |pred - image|^2 / (3 * #masked) + 1e-6.
+ * acc: 3 floats of workspace, ZERO on entry, kept for the backward call (acc[1] = #masked rays).
+ * backward: g_pred (R,3) = d_loss[0] * 2 (pred - image) / (3 * #masked) on masked rays, 0 elsewhere; d_loss is a device scalar. */
+int pnerf_masked_mse_forward(const float* pred, const float* image, const int8_t* ray_mask, int R, float* acc, float* loss_out,
+                             void* stream);
+int pnerf_masked_mse_backward(const float* pred, const float* image, const int8_t* ray_mask, int R, const float* acc,
+                              const float* d_loss, float* g_pred, void* stream);
+
 /* Confidence ("zero-one") loss term of SM:288-292,427-429 over ALL R''*SR*K slots (invalid slots
  * read point 0, SU:194): adds the value to loss_out[0] and its gradient to g_conf (N). */
 int pnerf_conf_loss(const float* conf, const int* sample_pidx, const int8_t* ray_mask, int R, int SR, int K,

@@ -190,6 +190,41 @@ __global__ void __launch_bounds__(256) conf_loss_kernel(const float* __restrict_
     if ((threadIdx.x & 31) == 0 && part != 0.f && loss_out) atomicAdd(loss_out, part * weight * inv_n);
 }
 
+// Masked-ray MSE of get_loss_dict (SM:415-426: MSELoss over the rays with ray_mask > 0, + 1e-6) and its gradient.  The torch
+// expression is seven elementwise / reduction launches forward and as many backward; a training step is launch-bound.
+// acc[0] = sum m (p - g)^2, acc[1] = sum m, acc[2] = block ticket (all zero on entry); the last block writes the loss.
+__global__ void __launch_bounds__(256) masked_mse_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ image,
+                                                              const int8_t* __restrict__ ray_mask, int R, float* __restrict__ acc,
+                                                              float* __restrict__ loss_out) {
+    float se = 0.f, cnt = 0.f;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+        if (ray_mask[r] <= 0) continue;
+        const float d0 = pred[3 * r] - image[3 * r], d1 = pred[3 * r + 1] - image[3 * r + 1], d2 = pred[3 * r + 2] - image[3 * r + 2];
+        se += d0 * d0 + d1 * d1 + d2 * d2;
+        cnt += 1.f;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    if ((threadIdx.x & 31) == 0 && cnt > 0.f) { atomicAdd(acc, se); atomicAdd(acc + 1, cnt); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned ticket = atomicAdd(reinterpret_cast<unsigned*>(acc + 2), 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const float a = *(volatile float*)acc, n = *(volatile float*)(acc + 1);
+            loss_out[0] = a / (3.f * n) + 1e-6f;        // no masked ray: 0 / 0 = NaN, as MSELoss over an empty selection
+        }
+    }
+}
+__global__ void __launch_bounds__(256) masked_mse_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ image,
+                                                              const int8_t* __restrict__ ray_mask, int R, const float* __restrict__ acc,
+                                                              const float* __restrict__ d_loss, float* __restrict__ g_pred) {
+    const float k = 2.f * d_loss[0] / (3.f * acc[1]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * R; i += gridDim.x * blockDim.x)
+        g_pred[i] = ray_mask[i / 3] > 0 ? k * (pred[i] - image[i]) : 0.f;
+}
+
 // Hole probing (original flow, neural_points_volumetric_model.py:331-362): per ray the sample of largest opacity, its position, the
 // distance to its nearest gathered neighbour and the (weight * confidence)-averaged attributes of its K neighbours -- the candidates
 // run/train_studio.py:335-444 turns into new neural points.  One warp per ray; lanes k < K own the neighbours of the chosen sample.
@@ -308,6 +343,24 @@ extern "C" int pnerf_probe(const pnerf_points* pts, const pnerf_camera* cam, con
     ProbeOut o = {max_opacity, max_loc, far_dist, avg_color, avg_dir, avg_conf, avg_embed};
     probe_kernel<<<ray_blocks(R), 256, 0, (cudaStream_t)stream>>>(make_ccam(cam), *mode, sample_loc, sample_valid, sigma, sample_pidx,
                                                                  pts->xyz, pts->embed, pts->color, pts->dir, pts->conf, R, SR, K, o);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_masked_mse_forward(const float* pred, const float* image, const int8_t* ray_mask, int R, float* acc, float* loss_out,
+                                       void* stream) {
+    if (R <= 0 || !pred || !image || !ray_mask || !acc || !loss_out) return PNERF_ERR_ARG;
+    const int blocks = min(kSMs * 2, (R + 255) / 256);
+    masked_mse_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, image, ray_mask, R, acc, loss_out);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_masked_mse_backward(const float* pred, const float* image, const int8_t* ray_mask, int R, const float* acc,
+                                        const float* d_loss, float* g_pred, void* stream) {
+    if (R <= 0 || !pred || !image || !ray_mask || !acc || !d_loss || !g_pred) return PNERF_ERR_ARG;
+    const int blocks = min(kSMs * 4, (3 * R + 255) / 256);
+    masked_mse_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, image, ray_mask, R, acc, d_loss, g_pred);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }
