@@ -26,6 +26,7 @@ from torch.nn import Parameter
 from . import native
 
 
+HIT_COMPACTION_MIN_RAYS = 32768       # bundles up to this size skip the hit-ray compaction (R -> R')
 RENDER_RAYS_PER_LAUNCH = 1 << 21   # rays per query launch in full-image rendering (memory knob only)
 
 
@@ -428,7 +429,9 @@ class PointNerf(nn.Module):
     def _get_outputs(self, ray_bundle, generator=None):
         c = self.config
         npnts = self.neural_points
-        q, origin, R_c2w, dirs = npnts.query(ray_bundle, generator=generator, compact=True)
+        # dropping the rays without an occupied position (R -> R') costs a host sync and six small launches: worth it for an image,
+        # not for a 4096-ray training batch, where those rays are nearly free in every kernel anyway
+        q, origin, R_c2w, dirs = npnts.query(ray_bundle, generator=generator, compact=len(ray_bundle) > HIT_COMPACTION_MIN_RAYS)
         mode = native.make_mode(c.flow, training=self.training, bg=self._background_color.tolist(), vsize_z=c.vsize[2])
         cfg = {"mode": mode, "camera": native.make_camera(origin, R_c2w)}
         args = (cfg, q, dirs, npnts.points_xyz, npnts.points_Rw2c, npnts.points_embeding.view(-1, c.point_features_dim),
@@ -442,13 +445,13 @@ class PointNerf(nn.Module):
             raise ValueError(c.precision)
         # rays dropped by the hit-ray compaction keep the background colour (fill_invalid, SM:491-504)
         R_total = q.R_total
-        src = self._background_color
-        key = (id(src), src._version, rgb.device, rgb.dtype)
-        hit = self.__dict__.get("_bg_dev")
-        if hit is None or hit[0] != key:             # one tiny host->device copy per background, not per call
-            hit = self.__dict__["_bg_dev"] = (key, src.to(device=self._device, dtype=rgb.dtype))
-        bg = hit[1]
-        rgb = bg.view(1, 3).expand(R_total, 3).index_copy(0, q.ray_index.long(), rgb)
+        if q.ray_index is not None:
+            src = self._background_color
+            key = (id(src), src._version, rgb.device, rgb.dtype)
+            hit = self.__dict__.get("_bg_dev")
+            if hit is None or hit[0] != key:             # one tiny host->device copy per background, not per call
+                hit = self.__dict__["_bg_dev"] = (key, src.to(device=self._device, dtype=rgb.dtype))
+            rgb = hit[1].view(1, 3).expand(R_total, 3).index_copy(0, q.ray_index.long(), rgb)
         lib = native._lib.load()
         R, SR = q.sample_valid.shape
         ray_mask = torch.empty((R,), dtype=torch.int8, device=self._device)
@@ -459,7 +462,10 @@ class PointNerf(nn.Module):
         native.check(lib.pnerf_ray_compact(native._ptr(q.sample_valid), R, SR, native._ptr(ray_mask), native._ptr(ray_index),
                                            native._ptr(n_rays), native._ptr(ws), ws_bytes, native._stream()), "pnerf_ray_compact")
         native.LAUNCHES["n"] += 3
-        full_mask = torch.zeros((R_total,), dtype=torch.int8, device=self._device).index_copy_(0, q.ray_index.long(), ray_mask)
+        if q.ray_index is not None:
+            full_mask = torch.zeros((R_total,), dtype=torch.int8, device=self._device).index_copy_(0, q.ray_index.long(), ray_mask)
+        else:
+            full_mask = ray_mask
         out = {"coarse_raycolor": rgb, "ray_mask": full_mask}
         if self.training:
             out["conf_coefficient"] = ConfCoefficient(npnts.points_conf, q.sample_pidx, ray_mask, n_rays)
@@ -514,10 +520,12 @@ class PointNerf(nn.Module):
                                      native._ptr(t["ray_max_far_dist"]), native._ptr(t["shading_avg_color"]),
                                      native._ptr(t["shading_avg_dir"]), native._ptr(t["shading_avg_conf"]),
                                      native._ptr(t["shading_avg_embedding"]), native._stream()), "pnerf_probe")
-        idx = q.ray_index.long()
         keep = out["ray_mask"].to(torch.float32)[:, None]
         for k, n in shapes.items():
-            out[k] = torch.zeros((q.R_total, n), dtype=torch.float32, device=dev).index_copy_(0, idx, t[k]) * keep
+            if q.ray_index is None:            # small bundle: no hit-ray compaction, the rows are the rays
+                out[k] = t[k] * keep
+            else:
+                out[k] = torch.zeros((q.R_total, n), dtype=torch.float32, device=dev).index_copy_(0, q.ray_index.long(), t[k]) * keep
         return out
 
     @torch.no_grad()

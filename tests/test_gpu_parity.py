@@ -277,6 +277,35 @@ def test_eval_mode_clamps_and_chunks():
     assert float(a["coarse_raycolor"].min()) >= 0 and float(a["coarse_raycolor"].max()) <= 1
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_hit_ray_compaction_changes_nothing(monkeypatch, precision):
+    """Bundles above HIT_COMPACTION_MIN_RAYS drop the rays without an occupied position before the query (the reference's R -> R'
+    step); smaller ones keep them.  Same pixels, masks and gradients either way."""
+    from pointnerf2studio_b200 import model as model_mod
+    s, cloud, cam, pix = _scene("config1")
+    W = of.FieldWeights.random(seed=6, scale=1.2)
+    m = _make_model(cloud, precision, "plugin", SR=s["SR"], K=s["K"], P=s["P"], weights=W)
+    m.train()
+    rb = _bundle(cam, pix)
+    gt = torch.rand((len(pix), 3), generator=torch.Generator().manual_seed(1)).cuda()
+    res = []
+    for min_rays in (1 << 30, 0):
+        monkeypatch.setattr(model_mod, "HIT_COMPACTION_MIN_RAYS", min_rays)
+        for p in m.parameters():
+            p.grad = None
+        out = m.get_outputs(rb)
+        assert (m._last_query.ray_index is None) == (min_rays > 0)
+        sum(m.get_loss_dict(out, {"image": gt}).values()).backward()
+        res.append((out["coarse_raycolor"].detach().clone(), out["ray_mask"].clone(),
+                    m.neural_points.points_embeding.grad.detach().clone(), m.mlp_base.layers[0].weight.grad.detach().clone()))
+    (c0, k0, ge0, gw0), (c1, k1, ge1, gw1) = res
+    assert torch.equal(k0, k1)
+    torch.testing.assert_close(c0, c1, rtol=0, atol=0)
+    # gradients: the same sums in a different atomic order
+    torch.testing.assert_close(ge0, ge1, rtol=1e-4, atol=1e-7 + 1e-5 * float(ge0.abs().max()))
+    torch.testing.assert_close(gw0, gw1, rtol=1e-3, atol=1e-6 + 1e-4 * float(gw0.abs().max()))
+
+
 def test_camera_host_hint_equals_device_readback():
     """metadata["camera_host"] (origin / rotation / near / far still on the caller's host) replaces the read-back of ray 0."""
     from pointnerf2studio_b200 import RayBundle
@@ -374,10 +403,13 @@ def test_probe_prune_grow(flow):
     np.testing.assert_array_equal(model.last_query_dense().sample_pidx.cpu().numpy(), pidx_n)
 
 
+@pytest.mark.parametrize("compaction", [True, False])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_model_all_rays_miss(precision):
+def test_model_all_rays_miss(precision, compaction, monkeypatch):
     """B.14 (i) through the model: a bundle whose rays all miss the cloud gives white pixels and an all-zero ray mask (SM:500-502),
-    in eval and in train mode (the hit-ray compaction leaves zero rows for every later stage)."""
+    in eval and in train mode, with the hit-ray compaction (which leaves zero rows for every later stage) and without it."""
+    from pointnerf2studio_b200 import model as model_mod
+    monkeypatch.setattr(model_mod, "HIT_COMPACTION_MIN_RAYS", 0 if compaction else 1 << 30)
     s, cloud, cam, _ = _scene("tinyP")
     pix = np.arange(96)                                   # image corner
     model = _make_model(cloud, precision, "plugin", SR=16, K=4, P=3)
