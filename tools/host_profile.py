@@ -47,6 +47,9 @@ def main():
     s = io.StringIO()
     pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(35)
     print(s.getvalue()[:6000])
+    s = io.StringIO()
+    pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(25)
+    print(s.getvalue()[:5000])
 
 
 if __name__ == "__main__":
