@@ -189,7 +189,10 @@ int pnerf_field_backward_f32(const pnerf_points* pts_h, const pnerf_camera* cam_
  * K-aggregation fused in one persistent kernel (no encoded input or activation ever reaches HBM), mlp_color +
  * rgb head in a second one.  `wpack` is the bf16 K-slab copy of the seven weight matrices made by
  * pnerf_tc_pack_weights (pnerf_tc_wpack_bytes() bytes; re-pack after every optimiser step).
- * Saves nothing (inference); sigma / rgb as in pnerf_field_forward_f32.  Training: pnerf_field_forward_tc_train below. */
+ * Saves nothing (inference); sigma / rgb as in pnerf_field_forward_f32.  Training: pnerf_field_forward_tc_train below.
+ * workspace: the aggregated features between the two kernels, 512 B per sample in whole 128-sample tiles
+ * (pnerf_field_tc_workspace_bytes(n_samples) bytes, 256-byte aligned); a caller bounds it by calling with pieces of the sample list
+ * (sample_ids + offset, n_samples of the piece) -- samples are independent. */
 int64_t pnerf_tc_wpack_bytes(void);
 int pnerf_tc_pack_weights(const pnerf_mlp* mlp_h, void* wpack, void* stream);
 int64_t pnerf_field_tc_workspace_bytes(int64_t n_samples);
