@@ -29,3 +29,27 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_has_the_contract_keys():
+    """The GPU arm on a reduced cloud (the keys do not depend on the size): metric / e2e / roofline / clocks / launches."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--points", "100000", "--steps", "3", "--warmup", "3",
+                          "--cpu-rays", "512"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["metric"] == "render rays/s" and line["unit"] == "rays/s" and line["n_gpus"] == 1 and line["scaling"] == "weak"
+    assert line["steps"] == 3 and line["warmup"] >= 3 and line["value"] > 0 and line["dtype"] == "bf16" and line["data"] == "synthetic"
+    assert line["gpu_launches"] > 0 and "workload" in line["config"] and "l2" in line["config"]
+    e2e = line["e2e"]
+    assert 0 < e2e["value"] <= line["value"] * 1.05 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
+    r = line["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert "traffic" in r and 0 < r["frac"] < 1
+    c = line["clocks"]
+    assert "sm_mhz" in c and "sm_max_mhz" in c and isinstance(c["reasons"], list)
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0
