@@ -748,6 +748,9 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   //
     return ok != 0;
 }
 
+#ifndef PNERF_COLOR_SPLIT
+#define PNERF_COLOR_SPLIT 1
+#endif
 template <bool SAVE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_kernel(const ColorParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -789,16 +792,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
         // the F part of the A operand (slabs 0..31 = 64 KB, contiguous in global memory) arrives by bulk copy; the copy for the slot's
         // next tile is issued as soon as the last layer's MMAs have released the buffer
         auto tile_of = [&](int j) { return 2 * (pair + j * n_pairs) + (int)rank; };
-        auto fetch = [&](int j) {
+        // in two halves: k-slabs 16..31 are free as soon as the tile's FIRST layer is done (layers 2 and 3 read slabs 0..15 only),
+        // slabs 0..15 after its last layer; the first half only announces its bytes, the second one arrives
+        auto fetch = [&](int j, int half) {
             const int ct = tile_of(j);
             if (ct * ROWS >= p.S) return;
-            mbar_arrive_expect_tx(&sm.f_full[s], (uint32_t)F_TILE_BYTES);
+            constexpr uint32_t HB = (uint32_t)(F_TILE_BYTES / 2);
+            if (half == 1) mbar_expect_tx(&sm.f_full[s], HB);
+            else mbar_arrive_expect_tx(&sm.f_full[s], HB);
 #pragma unroll
-            for (int q = 0; q < 4; q++)
-                bulk_g2s(sm.A[s] + q * (F_TILE_BYTES / 4), p.F + (int64_t)ct * F_TILE_BYTES + q * (F_TILE_BYTES / 4), (uint32_t)(F_TILE_BYTES / 4),
-                         &sm.f_full[s]);
+            for (int q = 0; q < 2; q++) {
+                const uint32_t off = (uint32_t)half * HB + (uint32_t)q * (HB / 2);
+                bulk_g2s(sm.A[s] + off, p.F + (int64_t)ct * F_TILE_BYTES + off, HB / 2, &sm.f_full[s]);
+            }
         };
-        if (row == 0 && s < n_my) fetch(s);
+        if (row == 0 && s < n_my) { fetch(s, 1); fetch(s, 0); }
         for (int j = s; j < n_my; j += 2) {
             const int ctile = tile_of(j);
             const int si = ctile * ROWS + row;
@@ -848,7 +856,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
             for (int L = 0; L < 3; L++) {
                 mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
                 tc_fence_after();
-                if (L == 2 && row == 0 && j + 2 < n_my) fetch(j + 2);     // the tile's last MMAs are done with the A buffer
+                if (row == 0 && j + 2 < n_my) {
+                    if (PNERF_COLOR_SPLIT) {
+                        if (L == 0) fetch(j + 2, 1);
+                        if (L == 2) fetch(j + 2, 0);     // the tile's last MMAs are done with the A buffer
+                    } else if (L == 2) {
+                        fetch(j + 2, 1); fetch(j + 2, 0);
+                    }
+                }
                 float r[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
                 for (int c0 = 0; c0 < HC; c0 += 32) {

@@ -28,6 +28,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// raise the expected transaction count of the current phase WITHOUT arriving (bytes announced ahead of the arrive.expect_tx)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 // try_wait with a suspend-time hint: the hardware parks the thread until the phase completes (or the hint, 10 ms, expires)
 // instead of returning after a short system-dependent time.  Without the hint the waiting warps of field_tc_kernel spun through
 // 8.1 G of its 14.4 G executed warp-instructions (ncu source page) and starved the working warps of issue slots.
