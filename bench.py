@@ -322,12 +322,13 @@ def main():
             model.get_outputs_for_camera_ray_bundle(rb_dev)
 
         def step_e2e():
-            rb = to_device(host, RayBundle)
+            # one camera per call: the directions are the per-ray input; origin / rotation / near / far are 14 floats
+            rb = RayBundle.for_camera(host[1].cuda(non_blocking=True), cam.origin, cam.R_c2w, cam.near, cam.far)
             o = model.get_outputs_for_camera_ray_bundle(rb)
             out_host.copy_(o["coarse_raycolor"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
-        h2d = sum(t.numel() * t.element_size() for t in host)
+        h2d = host[1].numel() * host[1].element_size() + 14 * 4
         d2h = out_host.numel() * 4
         metric = "render rays/s"
         workload = "render 800x800 view, 1M-point synthetic cloud, K=8, SR=80, voxel 0.008 (configs[1])"

@@ -42,6 +42,21 @@ class RayBundle:
     def __len__(self):
         return self.origins.shape[0]
 
+    @classmethod
+    def for_camera(cls, directions: torch.Tensor, origin, camrotc2w, near: float, far: float) -> "RayBundle":
+        """The rays of ONE camera -- all this path supports (origin, rotation, near and far are read from ray 0, SU:148-155).
+        `directions` (R,3) is on the device; origin (3,), camrotc2w (3,3), near, far are host values.  origins / nears / fars
+        are zero-copy (R,.) views of one 14-float upload instead of R copies, and the host values travel along as the
+        `camera_host` hint, so nothing is read back.  A server uploads 12 B per ray instead of 32."""
+        o = np.asarray(origin, dtype=np.float32).reshape(3)
+        r = np.asarray(camrotc2w, dtype=np.float32).reshape(3, 3)
+        R, dev = directions.shape[0], directions.device
+        cam = torch.from_numpy(np.concatenate([o, r.reshape(-1), np.asarray([near, far], dtype=np.float32)])).to(dev, non_blocking=True)
+        return cls(origins=cam[0:3].view(1, 3).expand(R, 3), directions=directions, nears=cam[12:13].view(1, 1).expand(R, 1),
+                   fars=cam[13:14].view(1, 1).expand(R, 1),
+                   metadata={"camrotc2w": cam[3:12].view(3, 3),
+                             "camera_host": {"origin": o, "camrotc2w": r, "near": float(near), "far": float(far)}})
+
 
 @dataclass
 class PointNerfConfig:

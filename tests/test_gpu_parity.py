@@ -322,6 +322,23 @@ def test_camera_host_hint_equals_device_readback():
     assert torch.equal(a["ray_mask"], b["ray_mask"])
 
 
+def test_ray_bundle_for_camera_equals_full_bundle():
+    """RayBundle.for_camera (12 B per ray uploaded, per-camera fields as zero-copy views) renders what the full bundle renders."""
+    from pointnerf2studio_b200 import RayBundle
+    s, cloud, cam, pix = _scene("tinyP")
+    model = _make_model(cloud, "fp32", "plugin", SR=16, K=4, P=3)
+    model.eval()
+    rb = _bundle(cam, pix)
+    rb2 = RayBundle.for_camera(rb.directions.clone(), cam.origin, cam.R_c2w, cam.near, cam.far)
+    assert len(rb2) == len(rb) and rb2.origins.shape == rb.origins.shape and rb2.nears.shape == rb.nears.shape
+    torch.testing.assert_close(rb2.origins, rb.origins, rtol=0, atol=0)
+    torch.testing.assert_close(rb2.fars, rb.fars, rtol=0, atol=0)
+    a = model.get_outputs_for_camera_ray_bundle(rb, chunk=100)
+    b = model.get_outputs_for_camera_ray_bundle(rb2, chunk=100)
+    torch.testing.assert_close(a["coarse_raycolor"], b["coarse_raycolor"], rtol=0, atol=0)
+    assert torch.equal(a["ray_mask"], b["ray_mask"])
+
+
 def test_in_kernel_jitter_replays_through_t_table():
     """The jittered selection generates its t mid-points in registers (Philox); pnerf_coarse_t exposes the same table.
     (a) the table follows RM:312-329 evaluated in float64 on the same uniforms, (b) the uniforms are uniform and differ
