@@ -45,7 +45,7 @@ def test_gpu_arm_line_has_the_contract_keys():
     assert line["steps"] == 3 and line["warmup"] >= 3 and line["value"] > 0 and line["dtype"] == "bf16" and line["data"] == "synthetic"
     assert line["gpu_launches"] > 0 and "workload" in line["config"] and "l2" in line["config"]
     e2e = line["e2e"]
-    assert 0 < e2e["value"] <= line["value"] * 1.05 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
+    assert e2e["value"] > 0 and e2e["unit"] == "rays/s" and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
     r = line["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert "traffic" in r and 0 < r["frac"] < 1
