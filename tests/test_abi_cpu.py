@@ -137,3 +137,21 @@ def test_argument_errors_are_return_codes_not_crashes():
     assert lib.pnerf_hit_rays(None, 0, None, None, None, 0, None) == ERR_ARG
     assert lib.pnerf_tc_wpack_bytes() == 573440 + 73728 + 2 * 32768
     assert lib.pnerf_field_tc_train_workspace_bytes(0, 8) > 0 and lib.pnerf_scan_workspace_bytes(1000) > 0
+
+
+def test_ray_bundle_for_camera_views_and_hint():
+    """RayBundle.for_camera: per-camera fields are zero-copy (R,.) views of one small tensor and the host values ride along."""
+    import numpy as np
+    import torch
+    from pointnerf2studio_b200 import RayBundle
+    d = torch.rand(7, 3)
+    rot = np.arange(9, dtype=np.float32).reshape(3, 3)
+    rb = RayBundle.for_camera(d, [1.0, 2.0, 3.0], rot, 2.0, 6.0)
+    assert len(rb) == 7 and rb.origins.shape == (7, 3) and rb.nears.shape == (7, 1) and rb.fars.shape == (7, 1)
+    assert rb.origins.stride(0) == 0 and rb.nears.stride(0) == 0                 # no R copies
+    assert rb.origins[4].tolist() == [1.0, 2.0, 3.0] and float(rb.nears[6]) == 2.0 and float(rb.fars[0]) == 6.0
+    assert torch.equal(rb.metadata["camrotc2w"], torch.from_numpy(rot))
+    hint = rb.metadata["camera_host"]
+    assert hint["near"] == 2.0 and hint["far"] == 6.0 and np.array_equal(hint["camrotc2w"], rot)
+    sl = RayBundle(rb.origins[2:5], rb.directions[2:5], rb.nears[2:5], rb.fars[2:5], rb.metadata)   # chunking keeps working
+    assert len(sl) == 3 and sl.origins.shape == (3, 3)
