@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- the Point-NeRF per-ray hot path on B200, measured on BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload render|train] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload render|train|scannet] [--precision bf16|fp32]
     python bench.py --impl reference ...        # the CPU arm (oracle port of the reference's algorithm)
 
-Workloads (BASELINE.json `configs`):
-  render (default, configs[1]) : NeRF-Synthetic-shaped render -- one 800x800 view (640 000 rays) of a ~1 M-point
-                                 synthetic neural cloud, K=8, SR=80, scaled voxel 0.008.  A step = one full image
-                                 through the hot path (coarse positions, sample selection, neighbour query, field
-                                 networks, compositing).  N GPUs: every rank renders its own view (ray-sharded by
-                                 view, cloud replicated, no data-path collective) -> weak scaling.
-  train  (configs[2])          : one training step fwd+bwd on 4096 rays per rank (point feature / colour / dir /
-                                 confidence grads + MLP grads), NCCL all-reduce of the gradients when N > 1.
+The default line (`--workload render`, BASELINE configs[1]) carries, besides the render measurement:
+  value / e2e / roofline / stages : one 800x800 view (640 000 rays) of a ~1 M-point synthetic neural cloud, K=8, SR=80,
+                                    scaled voxel 0.008 through the whole hot path (coarse positions, sample selection,
+                                    neighbour query, field networks, compositing).  N GPUs: every rank renders a DIFFERENT
+                                    view (azimuth 30 + 45 * rank degrees; ray-sharded by view, cloud replicated) and the
+                                    pixels of all views are all-gathered inside the timed region -> weak scaling.
+  train   (configs[2])            : fwd + bwd + gradient all-reduce (N > 1) + Adam on 4096 rays per rank, the reference's own
+                                    per-process batch (studio_config.py:20-21); `allreduce_ms` is reported separately.
+  parity  (N = 1)                 : the CPU oracle on a pixel sample of the SAME view with the very t table the GPU's in-kernel
+                                    jitter generated (pnerf_coarse_t): neighbour-index mismatches, pixel error, PSNR.  The same
+                                    CPU run is the `cpu_baseline`.
+  scannet (configs[3], N > 1 or --with-scannet) : ONE 1296x968 image of a 3 M-point cloud split over the ranks by interleaved
+                                    rows (strong scaling); device-timed with the pixel all-gather, end to end with every rank
+                                    copying its rows straight into one shared pinned host image.
 
-One JSON line on stdout (rank 0).  `value` = rays/s with the rays resident in HBM; `e2e` = the same through the
-public API with pinned-host rays and a host read-back of the pixels (loss for train) inside the timed region.
-The oracle is imported only by the `cpu_baseline` leg and by `--impl reference`.
+One JSON line on stdout (rank 0).  `value` = rays/s with the rays resident in HBM; `e2e` = the same through the public API with
+pinned-host rays and a host read-back of the pixels (loss for train) inside the timed region.  The oracle is imported only by
+the `cpu_baseline` / `parity` leg and by `--impl reference`.
 """
 from __future__ import annotations
 
@@ -39,6 +45,8 @@ N_POINTS = 1_000_000
 CLOUD_SEED = 1236          # 1234 + config id
 IMG = 800
 TRAIN_RAYS = 4096
+FIELD_FLOP_ROW = 542208.0 + 512.0     # per valid neighbour row
+COLOR_FLOP_SAMPLE = 137984.0          # per valid sample
 
 
 def load_peaks():
@@ -49,6 +57,18 @@ def load_peaks():
         return {"hbm": d["hbm_gbs"], "tensor_burst": d["bf16_tflops"], "tensor": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                 "src": "measured"}
     return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "src": "fallback"}
+
+
+def load_traffic(kernel, workload):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this very workload
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None when there is no capture for it."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(f"{workload}:{kernel}")
+    return (e["dram_bytes"], e["source"]) if e else (None, None)
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -95,8 +115,10 @@ class ClockSampler:
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        busy = [s for s, p in zip(sm, pw) if p > 400.0] or sm          # samples taken while the GPU was working
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "samples_under_load": len(busy) if pw else 0,
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -146,7 +168,7 @@ def to_device(ts, RayBundle):
     return RayBundle(origins=o, directions=d, nears=n, fars=f, metadata={"camrotc2w": rot, "camera_host": host_cam})
 
 
-def timed_steps(step_fn, K, flush, dist):
+def timed_steps(step_fn, K, flush, dist, per_step=None):
     """K steps, each bracketed by CUDA events on the launching stream; an L2 flush (not timed) runs between steps."""
     evs = []
     if dist is not None:
@@ -162,35 +184,81 @@ def timed_steps(step_fn, K, flush, dist):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    return sum(a.elapsed_time(b) for a, b in evs)    # ms over the K steps
+    ms = [a.elapsed_time(b) for a, b in evs]
+    if per_step is not None:
+        per_step.extend(ms)
+    return sum(ms)    # ms over the K steps
+
+
+def max_over_ranks(vals, dist):
+    t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(cloud, cam, weights, n_rays, SR, K, seed=5, mode="plugin"):
+def cpu_arm(cloud, cam, weights, pix, SR, K, seed=5, mode="plugin", t_mid=None, want_outputs=False):
     """The reference's algorithm on the host cores (oracle port): C grid querier (rebuilds the grid on every call,
-    as the reference does) + torch fp32 field networks + compositing, on `n_rays` pixels drawn uniformly from the
-    same view.  -> (seconds, rays)"""
+    as the reference does) + torch fp32 field networks + compositing on the pixels `pix` of the view.
+    `t_mid` (R,D): coarse t mid-points to use instead of drawing them with torch.rand (the parity leg passes the table
+    the GPU kernel generated).  -> (seconds, outputs or None)"""
     from oracle import field as of, grid_query as gq, query_c
     torch.set_num_threads(os.cpu_count() or 1)
-    rng = np.random.default_rng(seed)
-    pix = rng.choice(cam.H * cam.W, size=n_rays, replace=False)
     W = of.FieldWeights({k: v.clone() for k, v in weights.items()})
     pts = {"xyz": torch.from_numpy(cloud.xyz), "Rw2c": torch.from_numpy(cloud.Rw2c)}
     for k in ("embed", "color", "dir", "conf"):
         pts[k] = torch.from_numpy(getattr(cloud, k))
     rays = torch.from_numpy(cam.rays(pix))
+    origin = torch.from_numpy(cam.origin)
     t0 = time.perf_counter()
+    out = None
     with torch.no_grad():
         frame = gq.hyperparameters(cloud.xyz, [0.004] * 3, [2, 2, 2], [3, 3, 3], [-1.2] * 3 + [1.2] * 3)
-        raypos, _ = of.coarse_positions(torch.from_numpy(cam.origin), rays, 400, cam.near, cam.far, jitter=0.3,
-                                        generator=torch.Generator().manual_seed(seed))
+        if t_mid is None:
+            raypos, _ = of.coarse_positions(origin, rays, 400, cam.near, cam.far, jitter=0.3, generator=torch.Generator().manual_seed(seed))
+        else:
+            raypos = origin.float().view(1, 1, 3) + rays[:, None, :] * torch.as_tensor(t_mid)[:, :, None]     # RM:330
         pidx, loc, mask, hit = query_c.woord_query_grid_point_index(raypos.numpy(), cloud.xyz, [3, 3, 3], [3, 3, 3], SR, K, frame, 12,
                                                                     np.float32(0.016))
         cp, cl, cm = gq.compact_rays(pidx, loc, hit)
         if cp.shape[0] > 0:
-            of.render(pts, W, torch.from_numpy(cam.origin), rays, torch.from_numpy(cam.R_c2w), cp, cl, cm, 0.004, SR, mode=mode,
-                      training=False)
-    return time.perf_counter() - t0, n_rays
+            r = of.render(pts, W, origin, rays, torch.from_numpy(cam.R_c2w), cp, cl, cm, 0.004, SR, mode=mode, training=False)
+            if want_outputs:
+                out = {"pixels": r["coarse_raycolor"].numpy(), "pidx": pidx, "ray_mask": np.asarray(cm)}
+    return time.perf_counter() - t0, out
+
+
+def parity_leg(model, cloud, cam, weights, n_rays, SR, K, seed=5):
+    """The GPU path and the CPU oracle on the same `n_rays` pixels of `cam` with the same coarse t table.
+    -> (parity dict, cpu seconds)"""
+    from pointnerf2studio_b200 import RayBundle, native
+    rng = np.random.default_rng(seed)
+    pix = np.sort(rng.choice(cam.H * cam.W, size=n_rays, replace=False))
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        rb = RayBundle.for_camera(torch.from_numpy(cam.rays(pix)).cuda(), cam.origin, cam.R_c2w, cam.near, cam.far)
+        out = model.get_outputs_for_camera_ray_bundle(rb)
+        near, far, jitter, jseed = model.neural_points._last_jitter
+        t = native.coarse_t(near, far, jitter, jseed, n_rays, model.config.z_depth_dim, "cuda")
+        got_pix = out["coarse_raycolor"].cpu().numpy()
+        got_mask = out["ray_mask"].cpu().numpy()
+        got_pidx = model.last_query_dense().sample_pidx.cpu().numpy()
+        t = t.cpu().numpy()
+    model.train(was_training)
+    dt, ref = cpu_arm(cloud, cam, weights, pix, SR, K, t_mid=t, want_outputs=True)
+    mism = int((got_pidx != ref["pidx"]).sum())
+    mask_mism = int((got_mask.astype(bool) != ref["ray_mask"].astype(bool)).sum())
+    err = np.abs(got_pix - ref["pixels"])
+    hit = ref["ray_mask"].astype(bool)
+    mse = float((err ** 2).mean())
+    mse_hit = float((err[hit] ** 2).mean()) if hit.any() else 0.0
+    par = {"rays": int(n_rays), "rays_hit": int(hit.sum()), "idx_entries": int(got_pidx.size), "idx_mismatch": mism,
+           "ray_mask_mismatch": mask_mism, "max_abs_err": float(err.max()), "psnr_db": 10 * np.log10(1.0 / max(mse, 1e-20)),
+           "psnr_hit_rays_db": 10 * np.log10(1.0 / max(mse_hit, 1e-20)),
+           "against": "CPU oracle (fp32, C querier + torch field/compositing) fed the GPU kernel's own jittered t table"}
+    return par, dt
 
 
 def run_reference(args):
@@ -203,11 +271,12 @@ def run_reference(args):
     cam = view(0)
     weights = make_weights()
     n = args.cpu_rays
+    pick = lambda m, s: np.random.default_rng(s).choice(cam.H * cam.W, size=m, replace=False)
     for _ in range(max(args.warmup, 1) if args.warmup else 0):
-        cpu_arm(cloud, cam, weights, min(n, 256), 80, 8)
+        cpu_arm(cloud, cam, weights, pick(min(n, 256), 4), 80, 8)
     tot = 0.0
     for i in range(args.steps):
-        dt, _ = cpu_arm(cloud, cam, weights, n, 80, 8, seed=5 + i)
+        dt, _ = cpu_arm(cloud, cam, weights, pick(n, 5 + i), 80, 8, seed=5 + i)
         tot += dt
     v = n * args.steps / tot
     cores = os.cpu_count() or 1
@@ -223,6 +292,224 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ GPU arm: pieces
+class Ctx:
+    pass
+
+
+def query_stats(model, rb):
+    with torch.no_grad():
+        q, _, _, _ = model.neural_points.query(rb, want_stats=True)
+        torch.cuda.synchronize()
+        S = int(q.sample_valid.sum().item())
+        M = int((q.sample_pidx >= 0).sum().item())
+        filled = int(q.sample_cnt.sum().item())
+        rays_hit = int((q.sample_valid.sum(1) > 0).sum().item())
+        vis, cand = [int(x) for x in q.stats.tolist()]
+    return {"S": S, "M": M, "filled": filled, "rays_hit": rays_hit, "vis": vis, "cand": cand}
+
+
+def bench_render(c, cam, steps, warmup):
+    """configs[1]: one full 800x800 view per step on every rank (a different view per rank), pixels of all ranks all-gathered."""
+    from pointnerf2studio_b200 import RayBundle, native
+    model, dist, world = c.model, c.dist, c.world
+    model.eval()
+    pix = np.arange(cam.H * cam.W)
+    host = host_bundle(cam, pix)
+    rb_dev = to_device(host, RayBundle)
+    R = len(pix)
+    out_host = torch.empty((R, 3), dtype=torch.float32).pin_memory()
+    all_pix = torch.empty((world * R, 3), dtype=torch.float32, device="cuda") if dist is not None else None
+
+    def gather(rgb):
+        if dist is not None:       # every rank ends up with every view (what a device-side consumer of the frames needs)
+            dist.all_gather_into_tensor(all_pix, rgb.contiguous())
+
+    def step_dev():
+        gather(model.get_outputs_for_camera_ray_bundle(rb_dev)["coarse_raycolor"])
+
+    def step_e2e():
+        # one camera per call: the directions are the per-ray input; origin / rotation / near / far are 14 floats
+        rb = RayBundle.for_camera(host[1].cuda(non_blocking=True), cam.origin, cam.R_c2w, cam.near, cam.far)
+        o = model.get_outputs_for_camera_ray_bundle(rb)
+        gather(o["coarse_raycolor"])
+        out_host.copy_(o["coarse_raycolor"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    t0 = time.perf_counter()
+    model.neural_points.grid()
+    torch.cuda.synchronize()
+    grid_ms = 1e3 * (time.perf_counter() - t0)      # first build of the cached voxel grid (outside every timed region)
+    for _ in range(max(warmup, 1)):
+        step_dev()
+    torch.cuda.synchronize()
+    st = query_stats(model, rb_dev)
+    native.Timers.enabled = True
+    native.Timers.spans = []
+    l0 = native.LAUNCHES["n"]
+    per_step = []
+    ms_total = timed_steps(step_dev, steps, c.flush, dist, per_step)
+    launches = native.LAUNCHES["n"] - l0
+    spans = native.Timers.collect()
+    native.Timers.enabled = False
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed_steps(step_e2e, steps, c.flush, dist)
+    mine = ms_total
+    ms_total, ms_e2e = max_over_ranks([ms_total, ms_e2e], dist)
+    stage_ms = {k: sum(v) / steps for k, v in spans.items()}
+    h2d = host[1].numel() * host[1].element_size() + 14 * 4
+    d2h = out_host.numel() * 4
+    return {"R": R, "ms_total": ms_total, "ms_e2e": ms_e2e, "ms_this_rank": mine / steps, "stage_ms": stage_ms, "stats": st,
+            "launches": launches, "h2d": h2d, "d2h": d2h, "grid_build_ms": grid_ms, "rb_dev": rb_dev}
+
+
+def bench_train(c, cam, steps, warmup):
+    """configs[2]: fwd + bwd + gradient all-reduce + Adam (both groups) on 4096 rays per rank."""
+    from pointnerf2studio_b200 import RayBundle, native
+    from pointnerf2studio_b200.optim import make_optimizers
+    from pointnerf2studio_b200.parallel import allreduce_gradients
+    model, dist, world, rank = c.model, c.dist, c.world, c.rank
+    model.train()
+    rng = np.random.default_rng(100 + rank)
+    pix = rng.choice(cam.H * cam.W, size=TRAIN_RAYS, replace=False)
+    host = host_bundle(cam, pix)
+    rb_dev = to_device(host, RayBundle)
+    gt_host = torch.rand((TRAIN_RAYS, 3), generator=torch.Generator().manual_seed(9)).pin_memory()
+    gt_dev = gt_host.cuda()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opts, scheds = make_optimizers(model)       # the plugin's two Adam groups + exponential decay (studio_config.py:33-48)
+    ar_ev = []
+
+    def train_step(rb, gt, time_ar=False):
+        for p in params:
+            p.grad = None
+        out = model.get_outputs(rb)
+        ld = model.get_loss_dict(out, {"image": gt})
+        loss = sum(ld.values())
+        loss.backward()
+        if dist is not None:
+            if time_ar:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            allreduce_gradients(params, dist)
+            if time_ar:
+                b.record()
+                ar_ev.append((a, b))
+        for k in opts:
+            opts[k].step()
+            scheds[k].step()
+        return loss
+
+    def step_dev():
+        train_step(rb_dev, gt_dev)
+
+    def step_e2e():
+        rb = to_device(host, RayBundle)
+        loss = train_step(rb, gt_host.cuda(non_blocking=True))
+        loss.item()
+
+    # NCCL finishes its channel / buffer set-up over the first ~10 all-reduces of these tensors: untimed warm-up
+    n_warm = max(warmup, 3) + (10 if dist is not None else 0)
+    for _ in range(n_warm):
+        step_dev()
+    torch.cuda.synchronize()
+    st = query_stats(model, rb_dev)
+    native.Timers.enabled = True
+    native.Timers.spans = []
+    l0 = native.LAUNCHES["n"]
+    ms_total = timed_steps(step_dev, steps, c.flush, dist)
+    launches = native.LAUNCHES["n"] - l0
+    spans = native.Timers.collect()
+    native.Timers.enabled = False
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed_steps(step_e2e, steps, c.flush, dist)
+    # the collective on its own: a few more steps with an event pair around it (after a barrier, so that the wait for the slowest
+    # rank is not billed to it)
+    ar_ms = 0.0
+    if dist is not None:
+        for _ in range(5):
+            dist.barrier()
+            train_step(rb_dev, gt_dev, time_ar=True)
+        torch.cuda.synchronize()
+        ar_ms = statistics.median(a.elapsed_time(b) for a, b in ar_ev)
+    ms_total, ms_e2e, ar_ms = max_over_ranks([ms_total, ms_e2e, ar_ms], dist)
+    stage_ms = {k: sum(v) / steps for k, v in spans.items()}
+    field_ms = stage_ms.get("field", 0.0) + stage_ms.get("field_bwd", 0.0)
+    flops = 3.0 * (FIELD_FLOP_ROW * st["M"] + COLOR_FLOP_SAMPLE * st["S"])      # fwd + dgrad + wgrad
+    ach = flops / (field_ms * 1e-3) / 1e12 if field_ms > 0 else 0.0
+    n_pts = sum(p.numel() for p in model.get_param_groups()["neural_points"] if p.requires_grad)
+    n_mlp = sum(p.numel() for p in model.get_param_groups()["fields"] if p.requires_grad)
+    h2d = sum(t.numel() * t.element_size() for t in host) + gt_host.numel() * 4
+    rays_all = TRAIN_RAYS * world * steps
+    return {"metric": "train rays/s", "value": rays_all / (ms_total * 1e-3), "unit": "rays/s", "ms_per_step": ms_total / steps,
+            "steps": steps, "warmup": n_warm, "rays_per_step_per_gpu": TRAIN_RAYS,
+            "allreduce_ms": ar_ms, "allreduce_bytes": 4 * (n_pts + n_mlp) if dist is not None else 0,
+            "device_ms": {k: v for k, v in stage_ms.items()},
+            "e2e": {"value": rays_all / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "valid_samples_S": st["S"], "neighbour_rows_M": st["M"], "rays_hit": st["rays_hit"],
+            "roofline": {"kernel": "field networks fwd + dgrad + wgrad (tcgen05)", "bound": "tensor", "achieved": ach, "peak": c.peaks["tensor"],
+                         "unit": "TFLOP/s", "frac": ach / c.peaks["tensor"], "flops_per_step": flops, "ms_per_step": field_ms},
+            "workload": "training step fwd+bwd+all-reduce+Adam (fields 5e-4, neural points 2e-3), 4096 rays per rank drawn from the "
+                        "rank's own view, 1M-point synthetic cloud, K=8, SR=80 (configs[2])"}
+
+
+def bench_scannet(c, steps, warmup, n_points=3_000_000):
+    """configs[3]: ~3 M points, 1296 x 968 image, scaled voxel 0.016, radius 0.032, P = 30, SR = 24
+    (dev_scripts/w_scannet_etf/scene101_points.sh:24-37); ONE image split over the ranks by interleaved rows."""
+    from pointnerf2studio_b200 import PointNerf, PointNerfConfig, RayBundle
+    from pointnerf2studio_b200.parallel import SharedHostImage, gather_interleaved_image, interleaved_rows
+    from pointnerf2studio_b200.synth import make_camera, make_cloud
+    dist, world, rank = c.dist, c.world, c.rank
+    cloud = make_cloud(n_points, seed=1237, scaled_vsize=0.016, P=30, radii=(0.5, 0.72, 0.93))
+    cfg = PointNerfConfig(precision=c.precision, vsize=[0.008] * 3, P=30, SR=24)
+    model = PointNerf(cfg, state_dict=cloud.state_dict())
+    own = dict(model.named_parameters())
+    with torch.no_grad():
+        for k, v in c.weights.items():
+            own[k].copy_(v)
+    model.eval()
+    cam = make_camera(H=968, W=1296, focal=1170.0, azim_deg=30.0, elev_deg=20.0)      # the same view on every rank
+    n_img = cam.H * cam.W
+    rows = np.asarray(interleaved_rows(cam.H, rank, world))                          # rows rank, rank + N, ...: balanced work
+    pix = (rows[:, None] * cam.W + np.arange(cam.W)[None]).reshape(-1)
+    host = host_bundle(cam, pix)
+    rb_dev = to_device(host, RayBundle)
+    shared = SharedHostImage(cam.H, cam.W, rank, world, dist, tag=f"pnerf_bench_{os.environ.get('MASTER_PORT', '0')}")
+
+    def step_dev():
+        o = model.get_outputs_for_camera_ray_bundle(rb_dev)
+        if dist is not None:
+            gather_interleaved_image(o["coarse_raycolor"], cam.H, cam.W, dist)
+
+    def step_e2e():
+        rb = RayBundle.for_camera(host[1].cuda(non_blocking=True), cam.origin, cam.R_c2w, cam.near, cam.far)
+        o = model.get_outputs_for_camera_ray_bundle(rb)
+        shared.put_rows(o["coarse_raycolor"])          # this rank's rows straight into the one pinned host image: no collective
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(warmup, 1)):
+        step_dev()
+    ms_dev = timed_steps(step_dev, steps, c.flush, dist)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed_steps(step_e2e, steps, c.flush, dist)
+    ms_dev, ms_e2e = max_over_ranks([ms_dev, ms_e2e], dist)
+    shared.close()
+    del model
+    torch.cuda.empty_cache()
+    return {"metric": "render rays/s", "scaling": "strong", "value": n_img * steps / (ms_dev * 1e-3), "unit": "rays/s",
+            "ms_per_step": ms_dev / steps, "steps": steps,
+            "e2e": {"value": n_img * steps / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / steps,
+                    "h2d_bytes_per_step_per_gpu": host[1].numel() * 4 + 56, "d2h_bytes_per_step_per_gpu": len(pix) * 12,
+                    "how": "every rank uploads its rows' directions and copies its rendered rows into ONE shared pinned host image"},
+            "n_points": int(cloud.xyz.shape[0]), "rays_per_image": n_img,
+            "workload": "ScanNet-scale render: one 1296x968 image, rows interleaved over the ranks, device-timed with the pixel "
+                        "all-gather; 3M-point synthetic cloud, K=8, SR=24, voxel 0.016, P=30 (configs[3])"}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -233,8 +520,12 @@ def main():
     ap.add_argument("--workload", default="render", choices=["render", "train", "scannet"])
     ap.add_argument("--precision", default=None, choices=["bf16", "fp32"])
     ap.add_argument("--points", type=int, default=N_POINTS)
-    ap.add_argument("--cpu-rays", type=int, default=131072, help="pixels per step of the CPU arm")
+    ap.add_argument("--cpu-rays", type=int, default=131072, help="pixels per step of the CPU arm / parity leg")
+    ap.add_argument("--train-steps", type=int, default=0, help="timed steps of the train block (default: max(--steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--with-scannet", action="store_true", help="add the configs[3] block at N = 1 too (always on at N > 1)")
+    ap.add_argument("--no-scannet", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -253,211 +544,126 @@ def main():
         dist = dist_mod
     torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))     # N ranks share the host cores
     import importlib.util
-    from pointnerf2studio_b200 import PointNerf, PointNerfConfig, RayBundle, native
+    from pointnerf2studio_b200 import PointNerf, PointNerfConfig
     precision = args.precision
     if precision is None:
         precision = "bf16" if importlib.util.find_spec("pointnerf2studio_b200.native_tc") is not None else "fp32"
-    peaks = load_peaks()
 
-    weights = make_weights()
-    if args.workload == "scannet":
-        # BASELINE configs[3]: ~3 M points, 1296 x 968 image, scaled voxel 0.016, radius 0.032, P = 30, SR = 24
-        # (dev_scripts/w_scannet_etf/scene101_points.sh:24-37); ONE image split in row blocks over the ranks + all-gather
-        from pointnerf2studio_b200.synth import make_cloud
-        cloud = make_cloud(3_000_000 if args.points == N_POINTS else args.points, seed=1237, scaled_vsize=0.016, P=30,
-                           radii=(0.5, 0.72, 0.93))
-        cfg = PointNerfConfig(precision=precision, vsize=[0.008] * 3, P=30, SR=24)
-    else:
-        cloud, t_cloud = make_scene(args.points)
-        cfg = PointNerfConfig(precision=precision)    # plugin defaults: SR=80, K=8, P=12, vsize .004 x vscale 2, jitter 0.3
+    c = Ctx()
+    c.dist, c.world, c.rank, c.precision = dist, world, rank, precision
+    c.peaks = load_peaks()
+    c.weights = make_weights()
+    c.flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")     # 256 MB > 126 MB L2
+    train_steps = args.train_steps or max(args.steps, 20)
+
+    if args.workload == "scannet":       # stand-alone configs[3] line
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        blk = bench_scannet(c, args.steps, args.warmup, 3_000_000 if args.points == N_POINTS else args.points)
+        clocks = sampler.stop()
+        line = {"metric": blk["metric"], "value": blk["value"], "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 1), "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": blk["workload"], "n_points": blk["n_points"], "rays_per_image": blk["rays_per_image"],
+                           "l2": "256 MB flush write between timed steps (outside the event pairs)"},
+                "e2e": blk["e2e"], "clocks": clocks}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    cloud, _ = make_scene(args.points)
+    cfg = PointNerfConfig(precision=precision)    # plugin defaults: SR=80, K=8, P=12, vsize .004 x vscale 2, jitter 0.3
     model = PointNerf(cfg, state_dict=cloud.state_dict())
     own = dict(model.named_parameters())
     with torch.no_grad():
-        for k, v in weights.items():
+        for k, v in c.weights.items():
             own[k].copy_(v)
-    cam = view(0)      # weak scaling = fixed work per GPU: every rank renders the same view (training: its own pixels of it)
-    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")     # 256 MB > 126 MB L2
+    c.model = model
+    cam = view(rank)      # weak scaling: a different view per rank (training: the rank's own pixels of its view)
+    dtype = "bf16" if precision == "bf16" else "f32"
+    cores = os.cpu_count() or 1
 
-    if args.workload == "scannet":
-        from pointnerf2studio_b200.parallel import gather_interleaved_image, interleaved_rows
-        from pointnerf2studio_b200.synth import make_camera
-        model.eval()
-        cam = make_camera(H=968, W=1296, focal=1170.0, azim_deg=30.0, elev_deg=20.0)      # the same view on every rank
-        n_img = cam.H * cam.W
-        rows = np.asarray(interleaved_rows(cam.H, rank, world))                          # rows rank, rank + N, ...: balanced work
-        pix = (rows[:, None] * cam.W + np.arange(cam.W)[None]).reshape(-1)
-        host = host_bundle(cam, pix)
-        rb_dev = to_device(host, RayBundle)
-        R = len(pix)
-        out_host = torch.empty((n_img, 3), dtype=torch.float32).pin_memory()
+    if args.workload == "train":         # stand-alone configs[2] line
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        t = bench_train(c, cam, args.steps, args.warmup)
+        clocks = sampler.stop()
+        line = {"metric": "train rays/s", "value": t["value"], "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": t["warmup"],
+                "ms_per_step": t["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+                "data": "synthetic",
+                "config": {"workload": t["workload"], "n_points": int(cloud.xyz.shape[0]), "rays_per_step_per_gpu": TRAIN_RAYS,
+                           "l2": "256 MB flush write between timed steps (outside the event pairs)", "precision": precision},
+                "e2e": t["e2e"], "gpu_launches": t["gpu_launches"], "clocks": clocks, "roofline": t["roofline"], "train": t}
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
-        def render_rows(rb):
-            o = model.get_outputs_for_camera_ray_bundle(rb)
-            if dist is None:
-                return o["coarse_raycolor"]
-            return gather_interleaved_image(o["coarse_raycolor"], cam.H, cam.W, dist)
-
-        def step_dev():
-            render_rows(rb_dev)
-
-        def step_e2e():
-            img = render_rows(to_device(host, RayBundle))
-            out_host[:img.shape[0]].copy_(img, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-        h2d = sum(t.numel() * t.element_size() for t in host)
-        d2h = out_host.numel() * 4
-        metric = "render rays/s"
-        workload = ("ScanNet-scale render: one 1296x968 image, rows interleaved over the ranks + pixel all-gather, 3M-point "
-                    "synthetic cloud, K=8, SR=24, voxel 0.016, P=30 (configs[3])")
-    elif args.workload == "render":
-        model.eval()
-        pix = np.arange(cam.H * cam.W)
-        host = host_bundle(cam, pix)
-        rb_dev = to_device(host, RayBundle)
-        R = len(pix)
-        out_host = torch.empty((R, 3), dtype=torch.float32).pin_memory()
-
-        def step_dev():
-            model.get_outputs_for_camera_ray_bundle(rb_dev)
-
-        def step_e2e():
-            # one camera per call: the directions are the per-ray input; origin / rotation / near / far are 14 floats
-            rb = RayBundle.for_camera(host[1].cuda(non_blocking=True), cam.origin, cam.R_c2w, cam.near, cam.far)
-            o = model.get_outputs_for_camera_ray_bundle(rb)
-            out_host.copy_(o["coarse_raycolor"], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-        h2d = host[1].numel() * host[1].element_size() + 14 * 4
-        d2h = out_host.numel() * 4
-        metric = "render rays/s"
-        workload = "render 800x800 view, 1M-point synthetic cloud, K=8, SR=80, voxel 0.008 (configs[1])"
-    else:
-        model.train()
-        rng = np.random.default_rng(100 + rank)
-        pix = rng.choice(cam.H * cam.W, size=TRAIN_RAYS, replace=False)
-        host = host_bundle(cam, pix)
-        rb_dev = to_device(host, RayBundle)
-        R = TRAIN_RAYS
-        gt_host = torch.rand((R, 3), generator=torch.Generator().manual_seed(9)).pin_memory()
-        gt_dev = gt_host.cuda()
-        from pointnerf2studio_b200.optim import make_optimizers
-        from pointnerf2studio_b200.parallel import allreduce_gradients
-        params = [p for p in model.parameters() if p.requires_grad]
-        opts, scheds = make_optimizers(model)       # the plugin's two Adam groups + exponential decay (studio_config.py:33-48)
-
-        def train_step(rb, gt):
-            for p in params:
-                p.grad = None
-            out = model.get_outputs(rb)
-            ld = model.get_loss_dict(out, {"image": gt})
-            loss = sum(ld.values())
-            loss.backward()
-            if dist is not None:
-                allreduce_gradients(params, dist)
-            for k in opts:
-                opts[k].step()
-                scheds[k].step()
-            return loss
-
-        def step_dev():
-            train_step(rb_dev, gt_dev)
-
-        def step_e2e():
-            rb = to_device(host, RayBundle)
-            loss = train_step(rb, gt_host.cuda(non_blocking=True))
-            loss.item()
-
-        h2d = sum(t.numel() * t.element_size() for t in host) + gt_host.numel() * 4
-        d2h = 4
-        metric = "train rays/s"
-        workload = ("training step fwd+bwd+Adam (fields 5e-4, neural points 2e-3), 4096 rays per rank, 1M-point synthetic cloud, "
-                    "K=8, SR=80 (configs[2])")
-
-    # ---- warm-up (also builds the cached voxel grid) + occupancy statistics of this view (not timed)
-    # multi-rank training: NCCL finishes its channel / buffer set-up over the first ~10 all-reduces of these tensors (a 5-step run
-    # at 4 GPUs read 6.7 ms/step against 3.6 ms in steady state), so those steps are added to the untimed warm-up
-    n_warm = max(args.warmup, 1) + (10 if (dist is not None and args.workload == "train") else 0)
-    for _ in range(n_warm):
-        step_dev()
-    torch.cuda.synchronize()
-    with torch.no_grad():
-        q, _, _, _ = model.neural_points.query(rb_dev, want_stats=True)
-        torch.cuda.synchronize()
-        S = int(q.sample_valid.sum().item())
-        M = int((q.sample_pidx >= 0).sum().item())
-        filled = int(q.sample_cnt.sum().item())
-        rays_hit = int((q.sample_valid.sum(1) > 0).sum().item())
-        vis, cand = [int(x) for x in q.stats.tolist()]
-        del q
-
-    # ---- device-resident timing
+    # ---- default: render (value / e2e / roofline) + parity + train [+ scannet]
     sampler = ClockSampler(local_rank)
     sampler.start()
-    native.Timers.enabled = True
-    native.Timers.spans = []
-    l0 = native.LAUNCHES["n"]
-    ms_total = timed_steps(step_dev, args.steps, flush, dist)
-    launches = native.LAUNCHES["n"] - l0
-    spans = native.Timers.collect()
-    native.Timers.enabled = False
-    # ---- end to end through the public API with host buffers
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed_steps(step_e2e, args.steps, flush, dist)
+    r = bench_render(c, cam, args.steps, args.warmup)
     clocks = sampler.stop()
-
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
-    rays_all = (n_img if args.workload == "scannet" else R * world) * args.steps
-    value = rays_all / (ms_total * 1e-3)
-    e2e_value = rays_all / (ms_e2e * 1e-3)
-
-    # ---- roofline of the dominant kernel(s): the field networks (tensor bound); the query stage against HBM
-    stage_ms = {k: sum(v) / args.steps for k, v in spans.items()}
-    mult = 3.0 if args.workload == "train" else 1.0
-    flops = (542208.0 + 512.0) * M + 137984.0 * S
-    field_ms = stage_ms.get("field", 0.0) + (stage_ms.get("field_bwd", 0.0) if args.workload == "train" else 0.0)
-    ach_tf = flops * mult / (field_ms * 1e-3) / 1e12 if field_ms > 0 else 0.0
-    peak_tf = peaks["tensor"]
-    q_bytes = 12.0 * filled + 4.0 * vis + 16.0 * cand + 4.0 * cfg.K * filled
+    st, stage_ms, R = r["stats"], r["stage_ms"], r["R"]
+    rays_all = R * world * args.steps
+    value = rays_all / (r["ms_total"] * 1e-3)
+    e2e_value = rays_all / (r["ms_e2e"] * 1e-3)
+    flops = FIELD_FLOP_ROW * st["M"] + COLOR_FLOP_SAMPLE * st["S"]
+    field_ms = stage_ms.get("field", 0.0)
+    ach_tf = flops / (field_ms * 1e-3) / 1e12 if field_ms > 0 else 0.0
+    peak_tf = c.peaks["tensor"]
+    q_bytes = 12.0 * st["filled"] + 4.0 * st["vis"] + 16.0 * st["cand"] + 4.0 * cfg.K * st["filled"]
     q_ms = stage_ms.get("query", 0.0)
     q_gbs = q_bytes / (q_ms * 1e-3) / 1e9 if q_ms > 0 else 0.0
-    # dram__bytes_read + dram__bytes_write of field_tc_kernel<8,0> for one launch of this very workload (ncu --set full,
-    # profiles/r01_final_ncu_full.md): 0.58 GB read + 1.62 GB written, against 5.3 GB of algorithmic gather + output bytes
-    # (neighbouring samples share points, the gathers hit L2).  Only quoted for the workload it was captured on.
-    traffic = 2.194e9 if (args.workload == "render" and args.points == N_POINTS and precision == "bf16") else None
+    traffic, traffic_src = (load_traffic("field_tc_kernel", "render") if (args.points == N_POINTS and precision == "bf16") else (None, None))
     roofline = {"kernel": "field networks (gather + per-neighbour MLP + aggregation + colour MLP)", "bound": "tensor",
                 "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
-                "traffic_unit": "bytes of DRAM traffic per launch of field_tc_kernel (ncu, profiles/r01_final_ncu_full.md)",
-                "peak_source": peaks["src"] + " (sustained cuBLAS bf16)", "flops_per_launch": flops * mult, "ms_per_launch": field_ms}
-    stages = {"ms": stage_ms,
-              "query_hbm": {"achieved": q_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": q_gbs / peaks["hbm"],
-                            "algorithmic_bytes": q_bytes, "mean_voxels_visited": vis / max(filled, 1),
-                            "mean_candidates": cand / max(filled, 1)}}
+                "traffic_source": traffic_src, "peak_source": c.peaks["src"] + " (sustained cuBLAS bf16)",
+                "flops_per_launch": flops, "ms_per_launch": field_ms}
+    stages = {"ms": stage_ms, "grid_build_ms": r["grid_build_ms"],
+              "query_hbm": {"achieved": q_gbs, "peak": c.peaks["hbm"], "unit": "GB/s", "frac": q_gbs / c.peaks["hbm"],
+                            "algorithmic_bytes": q_bytes, "mean_voxels_visited": st["vis"] / max(st["filled"], 1),
+                            "mean_candidates": st["cand"] / max(st["filled"], 1)}}
+    per_rank_ms = [None] * world
+    if dist is not None:
+        dist.all_gather_object(per_rank_ms, r["ms_this_rank"])
+    else:
+        per_rank_ms = [r["ms_this_rank"]]
+    par = "one view per GPU (azimuth 30 + 45 * rank deg), cloud replicated" + ("; pixels of all views all-gathered inside the timed region"
+                                                                                   if world > 1 else "")
+    line = {"metric": "render rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+            "ms_per_step": r["ms_total"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic",
+            "config": {"workload": "render 800x800 view, 1M-point synthetic cloud, K=8, SR=80, voxel 0.008 (configs[1])",
+                       "n_points": int(cloud.xyz.shape[0]), "rays_per_step_per_gpu": R, "rays_hit": st["rays_hit"],
+                       "filled_slots": st["filled"], "valid_samples_S": st["S"], "neighbour_rows_M": st["M"], "cloud": cloud.stats,
+                       "l2": "256 MB flush write between timed steps (outside the event pairs)", "precision": precision,
+                       "jitter": cfg.jitter, "parallelism": f"ray-sharded x{world}: {par}", "ms_per_step_by_rank": per_rank_ms},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "ms_per_step": r["ms_e2e"] / args.steps},
+            "gpu_launches": r["launches"], "clocks": clocks, "roofline": roofline, "stages": stages}
 
-    scaling = "strong" if args.workload == "scannet" else "weak"      # scannet: one image of fixed size shared by all ranks
-    line = {"metric": metric, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": workload, "n_points": int(cloud.xyz.shape[0]), "rays_per_step_per_gpu": R,
-                       "rays_hit": rays_hit, "filled_slots": filled, "valid_samples_S": S, "neighbour_rows_M": M,
-                       "cloud": cloud.stats, "l2": "256 MB flush write between timed steps (outside the event pairs)",
-                       "precision": precision, "jitter": cfg.jitter, "parallelism": f"ray-sharded x{world}, cloud replicated; every rank works on the same view (fixed work per GPU)"},
-            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages}
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload != "scannet":
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n = args.cpu_rays
-        cpu_arm(cloud, cam, weights, 256, cfg.SR, cfg.K)                        # warm-up (builds nothing that persists)
-        dt, _ = cpu_arm(cloud, cam, weights, n, cfg.SR, cfg.K)
-        cores = os.cpu_count() or 1
+        cpu_arm(cloud, cam, c.weights, np.arange(256) * 97, cfg.SR, cfg.K)        # warm-up (builds nothing that persists)
+        parity, dt = parity_leg(model, cloud, cam, c.weights, n, cfg.SR, cfg.K)
+        line["parity"] = parity
         line["cpu_baseline"] = {"value": n / dt, "unit": "rays/s", "cores": cores, "kind": "port",
                                 "sample": f"{n} pixels drawn uniformly from the same 800x800 view ({dt:.1f} s); C grid querier (grid "
-                                          f"rebuilt per call like the reference) + torch fp32 field/compositing on {cores} threads"}
+                                          f"rebuilt per call like the reference) + torch fp32 field/compositing on {cores} threads, "
+                                          "fed the GPU kernel's jittered t table so that its pixels double as the parity check"}
+    if not args.no_train:
+        line["train"] = bench_train(c, cam, train_steps, args.warmup)
+    if (world > 1 or args.with_scannet) and not args.no_scannet:
+        del model
+        c.model = None
+        torch.cuda.empty_cache()
+        line["scannet"] = bench_scannet(c, args.steps, args.warmup)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -256,6 +256,16 @@ int pnerf_conf_loss(const float* conf, const int* sample_pidx, const int8_t* ray
                     float eps, float weight, const int* n_rays /* device R'' */, float* loss_out,
                     float* g_conf, float grad_scale, void* stream);
 
+/* ---------------------------------------------------------------- sharded image read-back (render partitioning)
+ * When ONE image is split over the ranks by interleaved rows, every rank copies the rows it rendered straight into one
+ * image in shared host memory (page-locked in each process with pnerf_host_register): row i of `src` (device, contiguous
+ * rows of row_bytes) lands at dst_h + i * dst_pitch.  One strided copy per rank, no collective and no staging buffer
+ * (the reference has no sharded render; its eval loop renders 2304-ray chunks on one GPU, studio_config.py:25). */
+int pnerf_host_register(void* host_ptr, int64_t bytes);
+int pnerf_host_unregister(void* host_ptr);
+int pnerf_copy_rows_to_host(void* dst_h, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes,
+                            int64_t n_rows, void* stream);
+
 /* ---------------------------------------------------------------- tensor-core plumbing self-test
  * D[128xN] = A[128xK] * W[NxK]^T (bf16 in, fp32 out) through tcgen05.mma / TMEM / bulk async copy.
  * A: bf16 row major; Wp: bf16 in the K-slab layout [K/8][N][8] (see csrc/umma.cuh). */

@@ -63,6 +63,9 @@ SIGNATURES = {
     "pnerf_version": (C.c_int, []),
     "pnerf_last_cuda_error": (C.c_char_p, []),
     "pnerf_device_check": (C.c_int, []),
+    "pnerf_host_register": (C.c_int, [C.c_void_p, C.c_int64]),
+    "pnerf_host_unregister": (C.c_int, [C.c_void_p]),
+    "pnerf_copy_rows_to_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "pnerf_bbox": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pnerf_grid_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
     "pnerf_grid_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,

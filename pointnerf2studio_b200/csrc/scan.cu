@@ -268,7 +268,25 @@ extern "C" int pnerf_gather_rays(const int* ray_index, int n_rays, int SR, int K
     return PNERF_OK;
 }
 
-extern "C" int pnerf_version(void) { return 100; }
+extern "C" int pnerf_version(void) { return 200; }
+extern "C" int pnerf_host_register(void* host_ptr, int64_t bytes) {
+    if (!host_ptr || bytes <= 0) return PNERF_ERR_ARG;
+    PNERF_CUDA(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return PNERF_OK;
+}
+extern "C" int pnerf_host_unregister(void* host_ptr) {
+    if (!host_ptr) return PNERF_ERR_ARG;
+    PNERF_CUDA(cudaHostUnregister(host_ptr));
+    return PNERF_OK;
+}
+extern "C" int pnerf_copy_rows_to_host(void* dst_h, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes,
+                                       int64_t n_rows, void* stream) {
+    if (!dst_h || !src || row_bytes <= 0 || n_rows < 0 || dst_pitch < row_bytes || src_pitch < row_bytes) return PNERF_ERR_ARG;
+    if (n_rows == 0) return PNERF_OK;
+    PNERF_CUDA(cudaMemcpy2DAsync(dst_h, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)row_bytes, (size_t)n_rows,
+                                 cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return PNERF_OK;
+}
 extern "C" const char* pnerf_last_cuda_error(void) { return g_last_error; }
 extern "C" int pnerf_device_check(void) {
     int dev = 0;

@@ -248,36 +248,25 @@ class NeuralPoints(nn.Module):
         ranges_tensor = torch.as_tensor(np.concatenate([f.lo, f.hi]), device=point_xyz_w_tensor.device)
         return ranges_tensor, vsize_np, f.dim
 
-    _CAM_CACHE = {}
-
     @staticmethod
     def camera_of(ray_bundle, with_near_far=False):
         """SU:148-155: one camera per call; rotation and origin come from ray 0 (and near / far, SU:154-155).
-        One device->host transfer for all of them."""
+        A bundle that carries the `camera_host` hint (RayBundle.for_camera, PointNerfDataManager, a server that just uploaded the
+        rays) costs nothing; otherwise ray 0 is read back with ONE 14-float device->host copy and the result is remembered ON
+        THE BUNDLE (its metadata dict), never keyed on device pointers: the caching allocator hands freed blocks back at the
+        same address, so a pointer / version key can alias two different cameras."""
         hint = ray_bundle.metadata.get("camera_host")
-        if hint is not None and (not with_near_far or ("near" in hint and "far" in hint)):
-            # a caller that still has the camera on the host (a server that just uploaded the rays) says so: no device->host
-            # read-back, hence no host sync between the upload and the first kernel launch
-            o = np.asarray(hint["origin"], dtype=np.float32).reshape(3).copy()
-            r = np.asarray(hint["camrotc2w"], dtype=np.float32).reshape(3, 3).copy()
-            return (o, r, float(hint["near"]), float(hint["far"])) if with_near_far else (o, r)
-        rot = ray_bundle.metadata["camrotc2w"]
-        rot = rot[0].view(3, 3) if rot.shape[0] != 3 else rot
-        # the same device tensors again (a bundle rendered / trained on repeatedly): reuse the host copy, no device->host sync
-        key = (ray_bundle.origins.data_ptr(), ray_bundle.origins._version, rot.data_ptr(), rot._version, with_near_far,
-               ray_bundle.nears.data_ptr() if with_near_far else 0, ray_bundle.fars.data_ptr() if with_near_far else 0)
-        hit = NeuralPoints._CAM_CACHE.get("k")
-        if hit == key:
-            h = NeuralPoints._CAM_CACHE["v"]
-        else:
-            parts = [ray_bundle.origins[0].detach().float().reshape(-1), rot.detach().float().reshape(-1)]
-            if with_near_far:
-                parts += [ray_bundle.nears[0].detach().float().reshape(-1)[:1], ray_bundle.fars[0].detach().float().reshape(-1)[:1]]
+        if hint is None or (with_near_far and not ("near" in hint and "far" in hint)):
+            rot = ray_bundle.metadata["camrotc2w"]
+            rot = rot[0].view(3, 3) if rot.shape[0] != 3 else rot
+            parts = [ray_bundle.origins[0].detach().float().reshape(-1), rot.detach().float().reshape(-1),
+                     ray_bundle.nears[0].detach().float().reshape(-1)[:1], ray_bundle.fars[0].detach().float().reshape(-1)[:1]]
             h = torch.cat(parts).cpu().numpy()
-            NeuralPoints._CAM_CACHE["k"], NeuralPoints._CAM_CACHE["v"] = key, h
-        if with_near_far:
-            return h[:3].copy(), h[3:12].reshape(3, 3).copy(), float(h[12]), float(h[13])
-        return h[:3].copy(), h[3:12].reshape(3, 3).copy()
+            hint = {"origin": h[:3].copy(), "camrotc2w": h[3:12].reshape(3, 3).copy(), "near": float(h[12]), "far": float(h[13])}
+            ray_bundle.metadata["camera_host"] = hint
+        o = np.asarray(hint["origin"], dtype=np.float32).reshape(3).copy()
+        r = np.asarray(hint["camrotc2w"], dtype=np.float32).reshape(3, 3).copy()
+        return (o, r, float(hint["near"]), float(hint["far"])) if with_near_far else (o, r)
 
     def coarse_t(self, R, near, far, jitter, generator=None):
         """t mid-points of near_far_linear_ray_generation (RM:312-329): (D,) when jitter == 0 else (R,D)."""

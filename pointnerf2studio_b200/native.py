@@ -275,13 +275,13 @@ _RW2C_HOST = {}
 
 
 def _rw2c_host(Rw2c):
-    """Host copy of points_Rw2c (a no-grad 3x3), fetched once per tensor version instead of one D2H sync per call."""
-    key = (Rw2c.data_ptr(), Rw2c._version)
-    hit = _RW2C_HOST.get("k")
-    if hit != key:
-        _RW2C_HOST["k"] = key
-        _RW2C_HOST["v"] = [float(v) for v in Rw2c.detach().reshape(-1).cpu().tolist()]
-    return _RW2C_HOST["v"]
+    """Host copy of points_Rw2c (a no-grad 3x3), fetched once per tensor version instead of one D2H sync per call.  The cache
+    entry holds a reference to the tensor it was read from, so its storage cannot be freed and handed to another tensor while
+    the entry is alive: (object identity, version) then identifies the contents."""
+    hit = _RW2C_HOST.get("e")
+    if hit is None or hit[0] is not Rw2c or hit[1] != Rw2c._version:
+        hit = _RW2C_HOST["e"] = (Rw2c, Rw2c._version, [float(v) for v in Rw2c.detach().reshape(-1).cpu().tolist()])
+    return hit[2]
 
 
 def make_points(xyz, embed, color, dirn, conf, Rw2c) -> Points:

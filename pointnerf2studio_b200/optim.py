@@ -46,6 +46,10 @@ class FusedAdam(torch.optim.Optimizer):
                     arr[j].n, arr[j].step, arr[j].lr = p.numel(), t, float(group["lr"])
                 check(lib.pnerf_adam_step(C.cast(arr, C.c_void_p), len(chunk), C.c_float(b1), C.c_float(b2), C.c_float(group["eps"]),
                                           C.c_float(grad_scale), stream), "pnerf_adam_step")
+            # the kernel writes the parameters through raw pointers: tell torch (and every cache keyed on `_version`, e.g. the
+            # bf16 weight pack of native_tc.packed_weights) that they changed
+            if segs:
+                torch.autograd.graph.increment_version([s[0] for s in segs])
         return None
 
 

@@ -37,10 +37,13 @@ def woord_query_grid_point_index(raypos_tensor, point_xyz_w_tensor, actual_numpo
                              dim=_as_np(scaled_vdim, np.int32))
     key = (xyz.data_ptr(), xyz._version, tuple(xyz.shape), frame.lo.tobytes(), frame.sv.tobytes(), frame.dim.tobytes(),
            int(P), qs.tobytes())
-    grid = _CACHE.get(key)
-    if grid is None:
+    hit = _CACHE.get(key)
+    # the entry keeps the very tensor it was built from alive (its storage cannot be recycled for another cloud while cached),
+    # so pointer + version identify the contents
+    if hit is None or hit[0].untyped_storage().data_ptr() != point_xyz_w_tensor.untyped_storage().data_ptr():
         _CACHE.clear()
-        grid = _CACHE[key] = native.VoxelGrid(xyz, frame, int(P), qs)
+        hit = _CACHE[key] = (point_xyz_w_tensor, native.VoxelGrid(xyz, frame, int(P), qs))
+    grid = hit[1]
     radius = float(radius_limit.item()) if isinstance(radius_limit, torch.Tensor) else float(radius_limit)
     raypos = raypos_tensor[0].contiguous().float()
     q = native.sample_and_query(grid, int(R), int(D), int(SR), int(K), int(ks[0]), radius, raypos=raypos)

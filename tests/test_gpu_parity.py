@@ -439,3 +439,60 @@ def test_model_all_rays_miss(precision, compaction, monkeypatch):
     out = model.probe(_bundle(cam, pix))
     assert float(out["ray_max_shading_opacity"].abs().sum()) == 0.0
     assert model.get_outputs_for_camera_ray_bundle(_bundle(cam, pix), chunk=40)["coarse_raycolor"].shape == (96, 3)
+
+
+def test_fresh_bundles_of_different_cameras_never_alias():
+    """The reference's datamanager builds a fresh bundle and a fresh (3,3) camrotc2w for every batch (studio_datamanager.py:79,100)
+    and the caching allocator hands the freed blocks back at the same addresses: the camera must be read from the bundle it
+    belongs to, never from a cache keyed on device pointers."""
+    from pointnerf2studio_b200 import RayBundle
+    from pointnerf2studio_b200.synth import make_camera
+    s, cloud, _, pix = _scene("config1")
+    W = of.FieldWeights.random(seed=3, scale=1.5)
+    model = _make_model(cloud, "fp32", "plugin", SR=s["SR"], K=s["K"], P=s["P"], weights=W).eval()
+    cams = [make_camera(azim_deg=a, elev_deg=e) for a, e in ((30.0, 20.0), (75.0, 35.0), (160.0, -10.0))]
+    want = []
+    with torch.no_grad():
+        for cam in cams:      # ground truth per camera: the host hint path, which reads nothing back
+            rb = RayBundle.for_camera(_cuda(cam.rays(pix)), cam.origin, cam.R_c2w, cam.near, cam.far)
+            want.append(model.get_outputs(rb)["coarse_raycolor"].clone())
+        assert float((want[0] - want[1]).abs().max()) > 1e-2
+        ptrs = set()
+        for cam, ref in zip(cams, want):
+            rb = _bundle(cam, pix)        # no hint: ray 0 has to be read back from THIS bundle
+            ptrs.add((rb.origins.data_ptr(), rb.metadata["camrotc2w"].data_ptr()))
+            got = model.get_outputs(rb)["coarse_raycolor"]
+            assert torch.equal(got, ref)
+            del rb, got
+    assert len(ptrs) < len(cams), "the allocator did not recycle the blocks; the test did not exercise the aliasing case"
+
+
+def test_fused_adam_updates_reach_the_bf16_forward():
+    """FusedAdam writes the parameters through raw pointers; the bf16 weight pack of the forward kernels has to follow
+    (it is cached per parameter version).  Three steps on the bf16 path must change the output and track the fp32 path."""
+    from pointnerf2studio_b200.optim import make_optimizers
+    s, cloud, cam, pix = _scene("config1")
+    pix = pix[:512]
+    W = of.FieldWeights.random(seed=5, scale=1.5)
+    gt = torch.rand((len(pix), 3), generator=torch.Generator().manual_seed(2)).cuda()
+    outs = {}
+    for precision in ("fp32", "bf16"):
+        model = _make_model(cloud, precision, "plugin", SR=24, K=s["K"], P=s["P"], weights=W).train()
+        opts, scheds = make_optimizers(model, lr_fields=5e-3, lr_points=2e-2)
+        rb = _bundle(cam, pix)
+        seq = []
+        for it in range(4):
+            for p in model.parameters():
+                p.grad = None
+            out = model.get_outputs(rb)
+            seq.append(out["coarse_raycolor"].detach().clone())
+            sum(model.get_loss_dict(out, {"image": gt}).values()).backward()
+            for k in opts:
+                opts[k].step()
+                scheds[k].step()
+        outs[precision] = seq
+    for precision, seq in outs.items():
+        assert float((seq[1] - seq[0]).abs().max()) > 1e-3, precision          # the first update is visible in the next forward
+        assert float((seq[3] - seq[1]).abs().max()) > 1e-3, precision
+    for a, b in zip(outs["fp32"], outs["bf16"]):
+        assert float((a - b).abs().max()) <= 3e-2

@@ -1,10 +1,15 @@
 """Tensor-core field path (csrc/field_tc.cu, bf16 operands / fp32 accumulation) against the fp32 oracle.
 
-Stated bf16 tolerance (BASELINE.json north_star): per-sample sigma within 3e-2 * max(sigma) and rgb within 2e-2
-absolute of the fp32 oracle; composited pixels within 2e-2 absolute and a PSNR of the bf16 image against the fp32
-image >= 40 dB (so that the PSNR of either against any ground truth differs by far less than 0.05 dB at the
-reference's 31-39 dB operating point).
+Stated bf16 tolerance (BASELINE.json north_star: "a stated bf16 tolerance with a PSNR delta <= 0.05 dB"): per-sample sigma
+within 3e-2 * max(sigma) and rgb within 2e-2 absolute of the fp32 oracle; composited pixels within 2e-2 absolute, and the PSNR
+of the bf16 image AGAINST the fp32 image >= PSNR_MUTUAL_MIN = 60 dB.  Why 60: with e = fp32 image - ground truth and
+d = bf16 image - fp32 image (rounding noise, uncorrelated with e), mse(bf16 - gt) = mse(e) + mse(d), so the PSNR against the
+ground truth drops by 10 log10(1 + mse(d) / mse(e)); keeping that <= 0.05 dB needs mse(d) <= 0.01158 mse(e), i.e. a mutual PSNR
+of at least PSNR(e) + 19.4 dB = 58.9 dB at the reference's best operating point (39.5 dB full image, pointnerf/out.txt:44-57;
+50.8 dB would do at its 31.4 dB ray-masked figure).  tests/test_gpu_fullsize.py applies the same bound to a full 800x800 view of
+the 1 M-point bench cloud with the shipped trained weights.
 """
+PSNR_MUTUAL_MIN = 60.0
 import numpy as np
 import pytest
 import torch
@@ -54,7 +59,7 @@ def test_tc_forward_matches_fp32_oracle(name, flow):
     print(f"{name}/{flow}: sigma err {es:.3e} (max sigma {smax:.3e}), rgb err {ec:.3e}, pixel err {err:.3e}, PSNR {psnr:.1f} dB")
     assert es <= 3e-2 * smax + 1e-3, (es, smax)
     assert ec <= 2e-2, ec
-    assert err <= 2e-2 and psnr >= 40.0, (err, psnr)
+    assert err <= 2e-2 and psnr >= PSNR_MUTUAL_MIN, (err, psnr)
 
 
 def test_tc_full_image_chunks_agree_with_fp32_kernels():
