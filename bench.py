@@ -11,7 +11,7 @@ The default line (`--workload render`, BASELINE configs[1]) carries, besides the
                                     view (azimuth 30 + 45 * rank degrees; ray-sharded by view, cloud replicated) and the
                                     pixels of all views are all-gathered inside the timed region -> weak scaling.
   train   (configs[2])            : fwd + bwd + gradient all-reduce (N > 1) + Adam on 4096 rays per rank, the reference's own
-                                    per-process batch (studio_config.py:20-21); `allreduce_ms` is reported separately.
+                                    per-process batch (studio_config.py:20-21); `update_ms` (exchange + Adam) is reported separately.
   parity  (N = 1)                 : the CPU oracle on a pixel sample of the SAME view with the very t table the GPU's in-kernel
                                     jitter generated (pnerf_coarse_t): neighbour-index mismatches, pixel error, PSNR.  The same
                                     CPU run is the `cpu_baseline`.
@@ -367,8 +367,7 @@ def bench_render(c, cam, steps, warmup):
 def bench_train(c, cam, steps, warmup):
     """configs[2]: fwd + bwd + gradient all-reduce + Adam (both groups) on 4096 rays per rank."""
     from pointnerf2studio_b200 import RayBundle, native
-    from pointnerf2studio_b200.optim import make_optimizers
-    from pointnerf2studio_b200.parallel import allreduce_gradients
+    from pointnerf2studio_b200.parallel import TrainEngine
     model, dist, world, rank = c.model, c.dist, c.world, c.rank
     model.train()
     rng = np.random.default_rng(100 + rank)
@@ -377,36 +376,14 @@ def bench_train(c, cam, steps, warmup):
     rb_dev = to_device(host, RayBundle)
     gt_host = torch.rand((TRAIN_RAYS, 3), generator=torch.Generator().manual_seed(9)).pin_memory()
     gt_dev = gt_host.cuda()
-    params = [p for p in model.parameters() if p.requires_grad]
-    opts, scheds = make_optimizers(model)       # the plugin's two Adam groups + exponential decay (studio_config.py:33-48)
-    ar_ev = []
-
-    def train_step(rb, gt, time_ar=False):
-        for p in params:
-            p.grad = None
-        out = model.get_outputs(rb)
-        ld = model.get_loss_dict(out, {"image": gt})
-        loss = sum(ld.values())
-        loss.backward()
-        if dist is not None:
-            if time_ar:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-            allreduce_gradients(params, dist)
-            if time_ar:
-                b.record()
-                ar_ev.append((a, b))
-        for k in opts:
-            opts[k].step()
-            scheds[k].step()
-        return loss
+    engine = TrainEngine(model, dist, exchange=c.exchange)     # the plugin's two Adam groups + exponential decay (studio_config.py:33-48)
 
     def step_dev():
-        train_step(rb_dev, gt_dev)
+        engine.step(rb_dev, gt_dev)
 
     def step_e2e():
         rb = to_device(host, RayBundle)
-        loss = train_step(rb, gt_host.cuda(non_blocking=True))
+        loss = engine.step(rb, gt_host.cuda(non_blocking=True))
         loss.item()
 
     # NCCL finishes its channel / buffer set-up over the first ~10 all-reduces of these tensors: untimed warm-up
@@ -425,18 +402,19 @@ def bench_train(c, cam, steps, warmup):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed_steps(step_e2e, steps, c.flush, dist)
-    # the collective on its own: a few more steps with an event pair around it (after a barrier, so that the wait for the slowest
-    # rank is not billed to it)
-    ar_ms = 0.0
-    if dist is not None:
-        for _ in range(5):
+    # gradient exchange + Adam + gradient reset on their own: a few more steps with an event pair around TrainEngine.update()
+    # (after a barrier, so that the wait for the slowest rank is not billed to it)
+    engine.timing = []
+    for _ in range(5):
+        if dist is not None:
             dist.barrier()
-            train_step(rb_dev, gt_dev, time_ar=True)
-        torch.cuda.synchronize()
-        ar_ms = statistics.median(a.elapsed_time(b) for a, b in ar_ev)
+        step_dev()
+    torch.cuda.synchronize()
+    ar_ms = statistics.median(a.elapsed_time(b) for a, b in engine.timing)
+    engine.timing = None
     ms_total, ms_e2e, ar_ms = max_over_ranks([ms_total, ms_e2e, ar_ms], dist)
     stage_ms = {k: sum(v) / steps for k, v in spans.items()}
-    field_ms = stage_ms.get("field", 0.0) + stage_ms.get("field_bwd", 0.0)
+    field_ms = stage_ms.get("render_fwd", 0.0) + stage_ms.get("render_bwd", 0.0)     # the two one-call launchers (pnerf_render_train_*)
     flops = 3.0 * (FIELD_FLOP_ROW * st["M"] + COLOR_FLOP_SAMPLE * st["S"])      # fwd + dgrad + wgrad
     ach = flops / (field_ms * 1e-3) / 1e12 if field_ms > 0 else 0.0
     n_pts = sum(p.numel() for p in model.get_param_groups()["neural_points"] if p.requires_grad)
@@ -445,12 +423,14 @@ def bench_train(c, cam, steps, warmup):
     rays_all = TRAIN_RAYS * world * steps
     return {"metric": "train rays/s", "value": rays_all / (ms_total * 1e-3), "unit": "rays/s", "ms_per_step": ms_total / steps,
             "steps": steps, "warmup": n_warm, "rays_per_step_per_gpu": TRAIN_RAYS,
-            "allreduce_ms": ar_ms, "allreduce_bytes": 4 * (n_pts + n_mlp) if dist is not None else 0,
+            "update_ms": ar_ms, "exchange": engine.exchange, "exchange_bytes": 4 * (n_pts + n_mlp) if dist is not None else 0,
+            "update_is": "gradient exchange over the ranks + Adam on both groups + gradient reset (TrainEngine.update); at 1 GPU it is the "
+                         "Adam pass alone, so the difference to the 1-GPU figure is the cost of the collective",
             "device_ms": {k: v for k, v in stage_ms.items()},
             "e2e": {"value": rays_all / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "valid_samples_S": st["S"], "neighbour_rows_M": st["M"], "rays_hit": st["rays_hit"],
-            "roofline": {"kernel": "field networks fwd + dgrad + wgrad (tcgen05)", "bound": "tensor", "achieved": ach, "peak": c.peaks["tensor"],
+            "roofline": {"kernel": "forward + backward launchers (selection, query, field networks fwd + dgrad + wgrad on tcgen05, compositing)", "bound": "tensor", "achieved": ach, "peak": c.peaks["tensor"],
                          "unit": "TFLOP/s", "frac": ach / c.peaks["tensor"], "flops_per_step": flops, "ms_per_step": field_ms},
             "workload": "training step fwd+bwd+all-reduce+Adam (fields 5e-4, neural points 2e-3), 4096 rays per rank drawn from the "
                         "rank's own view, 1M-point synthetic cloud, K=8, SR=80 (configs[2])"}
@@ -526,6 +506,7 @@ def main():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--with-scannet", action="store_true", help="add the configs[3] block at N = 1 too (always on at N > 1)")
     ap.add_argument("--no-scannet", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="gradient exchange of the train block at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -551,6 +532,7 @@ def main():
 
     c = Ctx()
     c.dist, c.world, c.rank, c.precision = dist, world, rank, precision
+    c.exchange = args.exchange
     c.peaks = load_peaks()
     c.weights = make_weights()
     c.flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")     # 256 MB > 126 MB L2

@@ -207,15 +207,50 @@ int pnerf_field_forward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h,
  * accumulates (+=) into the point gradients (may be NULL) and the MLP gradients: bf16 tcgen05 GEMMs for dgrad and wgrad of
  * mlp_base / mlp_head / mlp_color, fp32 accumulation.  `workspace` must be 256-byte aligned. */
 int64_t pnerf_field_tc_train_workspace_bytes(int64_t n_samples, int K);
+/* n_samples_dev (optional, device): the number of valid samples when the HOST does not know it (pnerf_sample_compact wrote it and
+ * nobody read it back).  `n_samples` is then a capacity (<= R*SR always works): workspace and grids are sized from it and every
+ * kernel clamps its tile loop to min(*n_samples_dev, n_samples) -- a training step never synchronises the host.
+ * points_done_event (optional, cudaEvent_t): recorded on `stream` right after the point gradients (g_embed .. g_conf) are complete
+ * and before the weight-gradient GEMMs, so that a data-parallel caller can start reducing them under the rest of the backward. */
 int pnerf_field_forward_tc_train(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const void* wpack,
                                  const pnerf_mode* mode_h, const float* dirs, const float* sample_loc, const int* sample_pidx,
-                                 const int* sample_ids, int n_samples, int SR, int K, float* sigma, float* rgb, void* workspace,
-                                 int64_t workspace_bytes, void* stream);
+                                 const int* sample_ids, int n_samples, const int* n_samples_dev, int SR, int K, float* sigma,
+                                 float* rgb, void* workspace, int64_t workspace_bytes, void* stream);
 int pnerf_field_backward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const pnerf_mode* mode_h,
                             const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int n_samples,
-                            int SR, int K, const float* d_sigma, const float* d_rgb, const float* rgb /* forward output, by slot */,
-                            float* g_embed, float* g_color, float* g_dir, float* g_conf, const pnerf_mlp_grad* g_mlp_h, void* workspace,
-                            int64_t workspace_bytes, void* stream);
+                            const int* n_samples_dev, int SR, int K, const float* d_sigma, const float* d_rgb,
+                            const float* rgb /* forward output, by slot */, float* g_embed, float* g_color, float* g_dir, float* g_conf,
+                            const pnerf_mlp_grad* g_mlp_h, void* workspace, int64_t workspace_bytes, void* points_done_event,
+                            void* stream);
+
+/* ---------------------------------------------------------------- one-call training pass (rows G0 .. C and their gradients)
+ * What PointNerf.get_outputs (SM:263-399) and torch autograd do per training step, as ONE host call per direction: sample
+ * selection (in-kernel jitter, or the (D,) / (R,D) table t_vals) -> neighbour query -> sample compaction -> tensor-core field
+ * networks (operands kept) -> compositing -> ray mask.  The host never learns R'' or S (device-side counts), so nothing
+ * synchronises.  All buffers are the caller's (torch allocates):
+ *   sample_loc (R,SR,3) f32, sample_cnt (R) i32, sample_pidx (R,SR,K) i32, sample_valid (R,SR) u8, sample_ids (R*SR) i32,
+ *   n_samples (1) i32, sigma (R,SR) f32, rgb (R,SR,3) f32 [both zero-filled here], out_rgb (R,3) f32, ray_mask (R) i8,
+ *   ray_index (R) i32, n_rays (1) i32; workspace: pnerf_field_tc_train_workspace_bytes(R*SR, K) bytes, 256-byte aligned, kept
+ *   until the backward call; scratch: pnerf_render_train_scratch_bytes(R, SR) bytes, may be reused right after each call.
+ * n_samples_cap: capacity of the sample workspace (pnerf_field_tc_train_workspace_bytes(n_samples_cap, K)); R * SR never overflows.
+ * phases: bit 0 = selection + query + sample compaction, bit 1 = field networks + compositing + ray mask; a caller that cannot
+ *   afford the worst-case workspace runs phase 1, reads n_samples back, and runs phase 2 with n_samples_cap = that count.
+ * backward: d_out (R,3) -> += into the point gradients (may be NULL) and the MLP gradients (as pnerf_field_backward_tc). */
+typedef struct {
+    float* sample_loc; int* sample_cnt; int* sample_pidx; uint8_t* sample_valid; int* sample_ids; int* n_samples;
+    float* sigma; float* rgb; float* out_rgb; int8_t* ray_mask; int* ray_index; int* n_rays;
+    void* workspace; int64_t workspace_bytes; void* scratch; int64_t scratch_bytes;
+} pnerf_render_buffers;
+int64_t pnerf_render_train_scratch_bytes(int R, int SR);
+int pnerf_render_train_forward(const pnerf_grid_view* grid_h, const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h,
+                               const void* wpack, const pnerf_mode* mode_h, const float* dirs, const float* t_vals, int t_stride,
+                               float near_t, float far_t, float jitter, uint64_t seed, int R, int D, int SR, int K, int kernel_size0,
+                               float radius, int n_samples_cap, int phases, const pnerf_render_buffers* buf_h, void* stream);
+int pnerf_render_train_backward(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const pnerf_mode* mode_h,
+                                const float* dirs, const float* d_out, int R, int SR, int K, int n_samples_cap,
+                                const pnerf_render_buffers* buf_h,
+                                float* g_embed, float* g_color, float* g_dir, float* g_conf, const pnerf_mlp_grad* g_mlp_h,
+                                void* points_done_event, void* stream);
 
 /* Profiling hook: when `buf` (device, pnerf_tc_trace_bytes() bytes, zero-filled) is set, CTA 0 of the next field_tc launches
  * appends clock64-stamped pipeline events per role warp (tools/tc_trace.py decodes them).  NULL switches it off. */
@@ -279,6 +314,26 @@ int pnerf_umma_selftest(const void* A, const void* Wp, float* D, int N, int K, v
 #define PNERF_ADAM_MAX_SEGS 32
 typedef struct { float* p; const float* g; float* m; float* v; int64_t n; int64_t step; float lr; } pnerf_adam_seg;
 int pnerf_adam_step(const pnerf_adam_seg* segs_h, int n_segs, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* Data-parallel optimiser step (training partitioning): gradient averaging over the ranks + Adam + parameter
+ * broadcast in ONE kernel over peer-mapped memory, replacing DDP's all-reduce (studio_pipeline.py:48-53) followed by a
+ * replicated torch.optim.Adam over both groups (studio_config.py:33-48).  Every rank keeps ALL its trainable parameters in one
+ * flat fp32 buffer and all gradients in another (same layout on every rank: neural-point tensors first, then the MLP tensors),
+ * both mapped into every peer (CUDA IPC / symmetric memory: p[w], g[w] = rank w's buffers as seen from this process).  This
+ * rank owns elements [lo, hi) (multiples of 4): it sums g[*][lo:hi), scales by grad_scale (1 / world), applies Adam with its
+ * slice of the moments m, v (hi - lo elements each: optimiser state is sharded) and writes the new values to p[*][lo:hi).
+ * Elements below `boundary` use lr[0] (neural points), the others lr[1] (fields).  world = 1: a plain fused Adam over one flat
+ * buffer.  The caller orders the launch between two cross-rank barriers (all gradients complete / all parameters delivered). */
+#define PNERF_DP_MAX_RANKS 8
+typedef struct {
+    float* p[PNERF_DP_MAX_RANKS];
+    const float* g[PNERF_DP_MAX_RANKS];
+    float* m; float* v;
+    int64_t lo, hi, boundary, step;
+    float lr[2];
+    int world, rank;
+} pnerf_dp_adam;
+int pnerf_dp_adam_step(const pnerf_dp_adam* h, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* Micro-benchmarks of the resources the tensor-core kernels lean on (one CTA per SM, all SMs): which = 0 tcgen05.mma
  * rate (param = N), 1 L2 -> shared bulk-copy ring (param = chunk bytes, src >= 557056 bytes), 2 tcgen05.ld rate

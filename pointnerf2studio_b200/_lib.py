@@ -54,6 +54,17 @@ class AdamSeg(C.Structure):
                 ("lr", C.c_float)]
 
 
+class DpAdam(C.Structure):
+    _fields_ = [("p", C.c_void_p * 8), ("g", C.c_void_p * 8), ("m", C.c_void_p), ("v", C.c_void_p), ("lo", C.c_int64), ("hi", C.c_int64),
+                ("boundary", C.c_int64), ("step", C.c_int64), ("lr", C.c_float * 2), ("world", C.c_int), ("rank", C.c_int)]
+
+
+class RenderBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("sample_loc", "sample_cnt", "sample_pidx", "sample_valid", "sample_ids", "n_samples", "sigma",
+                                          "rgb", "out_rgb", "ray_mask", "ray_index", "n_rays")] + \
+               [("workspace", C.c_void_p), ("workspace_bytes", C.c_int64), ("scratch", C.c_void_p), ("scratch_bytes", C.c_int64)]
+
+
 class PnerfError(RuntimeError):
     pass
 
@@ -98,12 +109,20 @@ SIGNATURES = {
                                            C.POINTER(MlpGrad), C.c_void_p, C.c_int64, C.c_void_p]),
     "pnerf_field_tc_train_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int]),
     "pnerf_field_forward_tc_train": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.c_void_p, C.POINTER(Mode),
-                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pnerf_field_backward_tc": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.POINTER(Mode),
-                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.POINTER(MlpGrad), C.c_void_p, C.c_int64, C.c_void_p]),
+                                          C.POINTER(MlpGrad), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pnerf_render_train_scratch_bytes": (C.c_int64, [C.c_int, C.c_int]),
+    "pnerf_render_train_forward": (C.c_int, [C.POINTER(GridView), C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.c_void_p,
+                                             C.POINTER(Mode), C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_uint64,
+                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                             C.POINTER(RenderBuffers), C.c_void_p]),
+    "pnerf_render_train_backward": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.POINTER(Mode), C.c_void_p, C.c_void_p,
+                                              C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(RenderBuffers), C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.POINTER(MlpGrad), C.c_void_p, C.c_void_p]),
     "pnerf_tc_set_trace": (C.c_int, [C.c_void_p]),
     "pnerf_tc_trace_bytes": (C.c_int64, []),
     "pnerf_tc_wpack_bytes": (C.c_int64, []),
@@ -118,6 +137,7 @@ SIGNATURES = {
                                            C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pnerf_umma_selftest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "pnerf_adam_step": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "pnerf_dp_adam_step": (C.c_int, [C.POINTER(DpAdam), C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "pnerf_tc_microbench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pnerf_probe": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mode), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

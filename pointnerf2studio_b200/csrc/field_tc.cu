@@ -111,7 +111,8 @@ struct FieldParams {
     const uint8_t* wpack;
     const float *wa, *ba;                    // density head (the four layer biases ride in the packed weights)
     Cam cam;
-    int S, SR, K, n_tiles;
+    int S, SR, K, n_tiles;          // S / n_tiles: host-side CAPACITY when S_dev is set (grid and workspace are sized from it)
+    const int* S_dev;               // device-side number of valid samples (<= S), or NULL: the host does not know S and never syncs for it
     float slope;
     int softplus, weight_conf;
     float* sigma;                   // (R*SR) by slot
@@ -168,13 +169,15 @@ __device__ __forceinline__ void pe(float x, float* out) {
 // ---------------------------------------------------------------------------------------------- encoder
 // The gather is a three-level dependent chain (sample id -> neighbour index -> point row).  The encoder runs it two tiles
 // ahead: ids of tile j+2 are loaded and the point rows of tile j+1 are prefetched into L2 while tile j is encoded.
+__device__ __forceinline__ int dyn_count(const int* n_dev, int cap) { return n_dev ? min(__ldg(n_dev), cap) : cap; }
+
 template <int KP>
-__device__ __forceinline__ void load_ids(const FieldParams& p, int tile, int row, int& slot, int& pidx) {
+__device__ __forceinline__ void load_ids(const FieldParams& p, int S, int tile, int row, int& slot, int& pidx) {
     constexpr int SPT = ROWS / KP;
     const int si = tile * SPT + row / KP;
     const int k = row % KP;
     slot = -1; pidx = -1;
-    if (si < p.S) {
+    if (si < S) {
         slot = __ldg(p.sample_ids + si);
         if (k < p.K) pidx = __ldg(p.sample_pidx + (int64_t)slot * p.K + k);
     }
@@ -527,7 +530,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();                      // 0 = leader (issues the MMAs)
     const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
-    const int n_super = (p.n_tiles + 1) >> 1;                     // 256-row super-tiles; this CTA takes tile 2*T + rank
+    const int S = dyn_count(p.S_dev, p.S);
+    const int n_tiles = (S + ROWS / KP - 1) / (ROWS / KP);
+    const int n_super = (n_tiles + 1) >> 1;                       // 256-row super-tiles; this CTA takes tile 2*T + rank
     const int n_my = n_super > pair ? (n_super - pair + n_pairs - 1) / n_pairs : 0;
     auto tile_of = [&](int j) { return 2 * (pair + j * n_pairs) + (int)rank; };
 
@@ -552,12 +557,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
         const int part = warp >> 2, erow = tid & 127;
         uint32_t ph[2] = {0, 0};
         int slot0, pidx0, slot1 = -1, pidx1 = -1;
-        load_ids<KP>(p, tile_of(0), erow, slot0, pidx0);
-        if (n_my > 1) load_ids<KP>(p, tile_of(1), erow, slot1, pidx1);
+        load_ids<KP>(p, S, tile_of(0), erow, slot0, pidx0);
+        if (n_my > 1) load_ids<KP>(p, S, tile_of(1), erow, slot1, pidx1);
         for (int j = 0; j < n_my; j++) {
             const int s = j & 1;
             int slot2 = -1, pidx2 = -1;
-            if (j + 2 < n_my) load_ids<KP>(p, tile_of(j + 2), erow, slot2, pidx2);
+            if (j + 2 < n_my) load_ids<KP>(p, S, tile_of(j + 2), erow, slot2, pidx2);
             if (ENC_PARTS == 1) { prefetch_point(p, pidx1, 0); prefetch_point(p, pidx1, 1); }
             else prefetch_point(p, pidx1, part);
             if (j >= 2) { mbar_wait(&sm.a_free[s], ph[s]); ph[s] ^= 1; }
@@ -720,7 +725,8 @@ struct ColorParams {
     const uint8_t* wpack_c;        // Wc1 | Wc2 | Wc3, each as two N-halves of k-slabs [k/8][64][8]
     const float *bc1, *bc2, *bc3, *wc4, *bc4;
     Cam cam;
-    int S, SR, n_tiles;
+    int S, SR, n_tiles;            // capacity when S_dev is set
+    const int* S_dev;
     float slope;
     float* rgb;                    // (R*SR,3) by slot
     uint8_t* csave;                // training: operand tiles [C0 | C1 | C2 | C3] per 128-sample tile (tc_layout.cuh), or NULL
@@ -758,7 +764,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
-    const int n_super = (p.n_tiles + 1) >> 1;
+    const int S = dyn_count(p.S_dev, p.S);
+    const int n_super = ((S + ROWS - 1) / ROWS + 1) >> 1;
     const int n_my = n_super > pair ? (n_super - pair + n_pairs - 1) / n_pairs : 0;
     if (tid == 0) {
         mbar_init(&sm.bar_w, 1);
@@ -796,7 +803,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
         // slabs 0..15 after its last layer; the first half only announces its bytes, the second one arrives
         auto fetch = [&](int j, int half) {
             const int ct = tile_of(j);
-            if (ct * ROWS >= p.S) return;
+            if (ct * ROWS >= S) return;
             constexpr uint32_t HB = (uint32_t)(F_TILE_BYTES / 2);
             if (half == 1) mbar_expect_tx(&sm.f_full[s], HB);
             else mbar_arrive_expect_tx(&sm.f_full[s], HB);
@@ -812,8 +819,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
             const int si = ctile * ROWS + row;
             uint4* grow = SAVE ? reinterpret_cast<uint4*>(p.csave + (int64_t)ctile * CSAVE_TILE_BYTES + row * 16) : nullptr;
             int slot = -1;
-            if (ctile * ROWS < p.S) { mbar_wait(&sm.f_full[s], fph); fph ^= 1; }
-            if (si < p.S) {
+            if (ctile * ROWS < S) { mbar_wait(&sm.f_full[s], fph); fph ^= 1; }
+            if (si < S) {
                 slot = __ldg(p.sample_ids + si);
                 if (SAVE) {
 #pragma unroll 8
@@ -1007,9 +1014,9 @@ namespace pnerf {
 // Fused per-neighbour networks (sigma by slot + F (S,256) bf16); with `save` != NULL every MMA operand is kept for the backward
 // pass (training); with `color` the tensor-core colour network follows (inference).
 int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack, const pnerf_mode* mode,
-                    const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S, int SR, int K,
-                    float* sigma, float* rgb, void* F, uint8_t* save, float* save_w, float* save_raw, bool color, uint8_t* csave,
-                    cudaStream_t st) {
+                    const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S, const int* S_dev,
+                    int SR, int K, float* sigma, float* rgb, void* F, uint8_t* save, float* save_w, float* save_raw, bool color,
+                    uint8_t* csave, cudaStream_t st) {
     const int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
     FieldParams p;
     p.xyz = pts->xyz; p.embed = pts->embed; p.color = pts->color; p.dir = pts->dir; p.conf = pts->conf;
@@ -1017,7 +1024,7 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     p.wpack = (const uint8_t*)wpack;
     p.wa = mlp->wa; p.ba = mlp->ba;
     p.cam = make_cam(pts, cam);
-    p.S = S; p.SR = SR; p.K = K;
+    p.S = S; p.S_dev = S_dev; p.SR = SR; p.K = K;
     const int spt = ROWS / KP;
     p.n_tiles = (S + spt - 1) / spt;
     p.slope = mode->lrelu_slope; p.softplus = mode->density_softplus; p.weight_conf = mode->weight_conf;
@@ -1056,7 +1063,7 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     c.F = p.F; c.sample_ids = sample_ids; c.dirs = dirs;
     c.wpack_c = (const uint8_t*)wpack + WPACK_FIELD_BYTES;
     c.bc1 = mlp->bc1; c.bc2 = mlp->bc2; c.bc3 = mlp->bc3; c.wc4 = mlp->wc4; c.bc4 = mlp->bc4;
-    c.cam = p.cam; c.S = S; c.SR = SR; c.n_tiles = (S + ROWS - 1) / ROWS;
+    c.cam = p.cam; c.S = S; c.S_dev = S_dev; c.SR = SR; c.n_tiles = (S + ROWS - 1) / ROWS;
     c.slope = mode->lrelu_slope; c.rgb = rgb; c.csave = csave;
     const int c_super = (c.n_tiles + 1) / 2;
     const int cgrid = 2 * (c_super < kSMs / 2 ? c_super : kSMs / 2);   // CTA pairs
@@ -1084,6 +1091,6 @@ extern "C" int pnerf_field_forward_tc(const pnerf_points* pts, const pnerf_camer
     if (S == 0) return PNERF_OK;
     if (!workspace || workspace_bytes < pnerf_field_tc_workspace_bytes(S)) return PNERF_ERR_WORKSPACE;
     if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;   // lrelu(x) = max(x, slope x)
-    return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, SR, K, sigma, rgb, workspace, nullptr,
-                           nullptr, nullptr, true, nullptr, (cudaStream_t)stream);
+    return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, nullptr, SR, K, sigma, rgb, workspace,
+                           nullptr, nullptr, nullptr, true, nullptr, (cudaStream_t)stream);
 }

@@ -53,6 +53,13 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
     return r;
 }
 
+// Device-side sample count: the host launches with a CAPACITY (grid, workspace carve) and never reads S back; every kernel clamps its
+// tile loop to the tiles that hold valid samples (spt samples per tile: 128 / KP for the per-neighbour tiles, 128 for the colour tiles).
+__device__ __forceinline__ int dyn_count(const int* n_dev, int cap) { return n_dev ? min(__ldg(n_dev), cap) : cap; }
+__device__ __forceinline__ int dyn_tiles(const int* n_dev, int cap_tiles, int spt) {
+    return n_dev ? min((__ldg(n_dev) + spt - 1) / spt, cap_tiles) : cap_tiles;
+}
+
 // ---------------------------------------------------------------------------------------------- transposed weight pack
 // Bt[k/8][n][8] with Bt(n, k) = W[k][n]: k = output feature of the forward layer (256), n = input feature (first `n_cols`).
 struct PackT { const float* w; int in_dim, n_cols; int64_t off; int out_dim; };
@@ -72,7 +79,7 @@ struct AggBwd {
     const uint8_t* save; const float *save_w, *save_raw;
     const int* sample_ids; const float* d_sigma; const float* dF; int ldF;
     const float* wa;
-    int S, KP, n_tiles, softplus; float slope;
+    int S, KP, n_tiles, softplus; float slope; const int* S_dev;
     uint8_t* d4; float *dwa, *dba, *dw_rows;
 };
 __global__ void __launch_bounds__(128) agg_bwd_kernel(const AggBwd p) {
@@ -82,12 +89,13 @@ __global__ void __launch_bounds__(128) agg_bwd_kernel(const AggBwd p) {
     s_wa[row] = p.wa[row]; s_wa[row + 128] = p.wa[row + 128];
     float acc_wa[2] = {0.f, 0.f}, acc_ba = 0.f;
     const int spt = ROWS / p.KP;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int S = dyn_count(p.S_dev, p.S), n_tiles = dyn_tiles(p.S_dev, p.n_tiles, spt);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();
         const int64_t grow = (int64_t)tile * ROWS + row;
         const int si = tile * spt + row / p.KP;
         const float w = p.save_w[grow], raw = p.save_raw[grow];
-        const bool live = si < p.S;
+        const bool live = si < S;
         const float ds = live ? p.d_sigma[p.sample_ids[si]] : 0.f;
         const float a = p.softplus ? softplus_f(raw - 1.f) : fmaxf(raw, 0.f);
         const float dact = p.softplus ? sigmoid_f(raw - 1.f) : (raw > 0.f ? 1.f : 0.f);
@@ -140,6 +148,7 @@ struct GemmP {
     uint8_t* out_bf; int64_t out_stride;             // bf16 tile output, or
     float* out_f32; int ld_f32;                      // fp32 row-major output (row = tile * 128 + r)
     const uint8_t* w; int N; int ks; int n_tiles; float slope;
+    const int* S_dev; int spt;                       // device-side sample count and samples per tile (n_tiles is the capacity)
 };
 struct GemmSmem {
     uint8_t W[32 * HID * 16];
@@ -152,7 +161,8 @@ __global__ void __launch_bounds__(256, 1) tile_gemm_kernel(const GemmP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_my = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_tiles = dyn_tiles(p.S_dev, p.n_tiles, p.spt);
+    const int n_my = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (tid == 0) {
         mbar_init(&sm.w_bar, 1); mbar_init(&sm.a_full, 1); mbar_init(&sm.a_free, 1);
         for (int b = 0; b < 2; b++) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 4); }
@@ -236,10 +246,10 @@ struct WgJob {
     const uint8_t* d; int64_t d_stride; int d_slab0;          // gradient tiles: base, tile stride, first k-slab of this job's 128 output features
     const uint8_t* x; int64_t x_stride; int x_slab0, xslabs;  // the layer's input tiles
     float* dW; int in_dim, out0;                              // (out, in_dim) fp32, accumulated into; first output feature of the job
-    int n_tiles;
+    int n_tiles, spt;                                         // tile capacity, samples per tile
 };
 constexpr int WG_MAX_JOBS = 12;
-struct WgradP { WgJob j[WG_MAX_JOBS]; int n_jobs; };
+struct WgradP { WgJob j[WG_MAX_JOBS]; int n_jobs; const int* S_dev; };
 struct WgSmem {
     uint8_t D[2][16 * SLAB];        // one 128-column half of a delta tile: M = 128 output features, K = 128 rows
     uint8_t X[2][36 * SLAB];        // the layer's input tile: N = up to 288 input features, K = 128 rows
@@ -253,7 +263,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const WgJob& jb = p.j[(int)blockIdx.x % p.n_jobs];
     const int part = (int)blockIdx.x / p.n_jobs, parts = (int)gridDim.x / p.n_jobs;
-    const int n_my = jb.n_tiles > part ? (jb.n_tiles - part + parts - 1) / parts : 0;
+    const int n_tiles = dyn_tiles(p.S_dev, jb.n_tiles, jb.spt);
+    const int n_my = n_tiles > part ? (n_tiles - part + parts - 1) / parts : 0;
     const int xslabs = jb.xslabs;
     if (tid == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
@@ -322,8 +333,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
 
 // ---------------------------------------------------------------------------------------------- bias gradients
 // db_L[c] = sum over rows of delta_L[r][c].  Thread = (slab, 16-row group); block = one tile at a time.
-struct ColsumJob { const uint8_t* d; int64_t d_stride; int n_slabs; float* db; int n_tiles; };
-struct ColsumP { ColsumJob j[7]; };
+struct ColsumJob { const uint8_t* d; int64_t d_stride; int n_slabs; float* db; int n_tiles, spt; };
+struct ColsumP { ColsumJob j[7]; const int* S_dev; };
 __global__ void __launch_bounds__(256) colsum_kernel(const ColsumP p) {
     __shared__ float s_part[8][HID];
     const ColsumJob jb = p.j[blockIdx.y];
@@ -331,7 +342,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColsumP p) {
     const int slab = t >> 3, rg = t & 7;
     float acc[8] = {};
     if (slab < jb.n_slabs) {
-        for (int tile = blockIdx.x; tile < jb.n_tiles; tile += gridDim.x) {
+        const int n_tiles = dyn_tiles(p.S_dev, jb.n_tiles, jb.spt);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint4* src = reinterpret_cast<const uint4*>(jb.d + (int64_t)tile * jb.d_stride + (int64_t)slab * SLAB) + rg * 16;
 #pragma unroll 4
             for (int r = 0; r < 16; r++) {
@@ -355,7 +367,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColsumP p) {
 // rgb = sigmoid(Wc4 c3 + bc4) * 1.002 - 0.001 (SM:358-359): d raw, delta_c3 = lrelu'(c3) * (Wc4^T d raw) per sample; d Wc4, d bc4.
 struct HeadBwd {
     const uint8_t* csave; const int* sample_ids; const float *d_rgb, *rgb, *wc4;
-    int S, n_tiles; float slope;
+    int S, n_tiles; float slope; const int* S_dev;
     uint8_t* d3; float *dwc4, *dbc4;
 };
 __global__ void __launch_bounds__(128) color_head_bwd_kernel(const HeadBwd p) {
@@ -365,11 +377,12 @@ __global__ void __launch_bounds__(128) color_head_bwd_kernel(const HeadBwd p) {
 #pragma unroll
     for (int j = 0; j < 3; j++) s_w4[j][row] = p.wc4[j * HC + row];
     float gw[3] = {0.f, 0.f, 0.f}, gb = 0.f;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int S = dyn_count(p.S_dev, p.S), n_tiles = dyn_tiles(p.S_dev, p.n_tiles, ROWS);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();
         const int si = tile * ROWS + row;
         float dz[3] = {0.f, 0.f, 0.f};
-        if (si < p.S) {
+        if (si < S) {
             const int slot = p.sample_ids[si];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -418,7 +431,7 @@ struct ScatterP {
     const uint8_t* d3;              // delta_3 tiles: gradient of mlp_head layer-0 pre-activations
     const float* w3;                // mlp_head.layers.0 weight (256, 263): columns 256..262 multiply the 7 extras
     const float *dw_rows, *save_w;
-    int S, SR, K, KP, n_tiles, weight_conf;
+    int S, SR, K, KP, n_tiles, weight_conf; const int* S_dev;
     float *g_embed, *g_color, *g_dir, *g_conf;
 };
 __global__ void __launch_bounds__(128) scatter_kernel(const ScatterP p) {
@@ -427,9 +440,10 @@ __global__ void __launch_bounds__(128) scatter_kernel(const ScatterP p) {
     __syncthreads();
     const int row = threadIdx.x;
     const int spt = ROWS / p.KP;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int S = dyn_count(p.S_dev, p.S), n_tiles = dyn_tiles(p.S_dev, p.n_tiles, spt);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int si = tile * spt + row / p.KP, k = row % p.KP;
-        if (si >= p.S || k >= p.K) continue;
+        if (si >= S || k >= p.K) continue;
         const int slot = p.sample_ids[si];
         const int pt = p.sample_pidx[(int64_t)slot * p.K + k];
         if (pt < 0) continue;
@@ -535,22 +549,22 @@ extern "C" int64_t pnerf_field_tc_train_workspace_bytes(int64_t n_samples, int K
 
 extern "C" int pnerf_field_forward_tc_train(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack,
                                             const pnerf_mode* mode, const float* dirs, const float* sample_loc, const int* sample_pidx,
-                                            const int* sample_ids, int S, int SR, int K, float* sigma, float* rgb, void* workspace,
-                                            int64_t workspace_bytes, void* stream) {
+                                            const int* sample_ids, int S, const int* n_samples_dev, int SR, int K, float* sigma, float* rgb,
+                                            void* workspace, int64_t workspace_bytes, void* stream) {
     if (!pts || !cam || !mlp || !wpack || !mode || S < 0 || K <= 0 || K > 32 || SR <= 0) return PNERF_ERR_ARG;
     if (S == 0) return PNERF_OK;
     if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < pnerf_field_tc_train_workspace_bytes(S, K)) return PNERF_ERR_WORKSPACE;
     if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;
     TrainWs w = carve_train(workspace, S, K);
-    return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, SR, K, sigma, rgb, w.F, w.save, w.save_w,
-                           w.save_raw, true, w.csave, (cudaStream_t)stream);
+    return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, n_samples_dev, SR, K, sigma, rgb, w.F, w.save,
+                           w.save_w, w.save_raw, true, w.csave, (cudaStream_t)stream);
 }
 
 extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const pnerf_mode* mode,
                                        const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S,
-                                       int SR, int K, const float* d_sigma, const float* d_rgb, const float* rgb, float* g_embed,
-                                       float* g_color, float* g_dir, float* g_conf, const pnerf_mlp_grad* gm, void* workspace,
-                                       int64_t workspace_bytes, void* stream) {
+                                       const int* S_dev, int SR, int K, const float* d_sigma, const float* d_rgb, const float* rgb,
+                                       float* g_embed, float* g_color, float* g_dir, float* g_conf, const pnerf_mlp_grad* gm,
+                                       void* workspace, int64_t workspace_bytes, void* points_done_event, void* stream) {
     if (!pts || !cam || !mlp || !mode || !gm || S < 0 || K <= 0 || K > 32 || SR <= 0 || !d_sigma || !d_rgb || !rgb) return PNERF_ERR_ARG;
     if (S == 0) return PNERF_OK;
     if (!workspace || ((uintptr_t)workspace & 255) || workspace_bytes < pnerf_field_tc_train_workspace_bytes(S, K)) return PNERF_ERR_WORKSPACE;
@@ -571,8 +585,9 @@ extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_came
     const size_t gsm = sizeof(GemmSmem);
     PNERF_CUDA(cudaFuncSetAttribute(tile_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm));
     auto gemm = [&](const uint8_t* in, int64_t in_stride, int ks, const uint8_t* mask, int64_t mask_stride, uint8_t* out_bf,
-                    int64_t out_stride, float* out_f32, int ld, int64_t wb, int N, int tiles) -> int {
+                    int64_t out_stride, float* out_f32, int ld, int64_t wb, int N, int tiles, int spt) -> int {
         GemmP g;
+        g.S_dev = S_dev; g.spt = spt;
         g.in = in; g.in_stride = in_stride; g.ks = ks; g.mask = mask; g.mask_stride = mask_stride;
         g.out_bf = out_bf; g.out_stride = out_stride; g.out_f32 = out_f32; g.ld_f32 = ld;
         g.w = w.wbwd + wb; g.N = N; g.n_tiles = tiles; g.slope = slope;
@@ -584,43 +599,57 @@ extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_came
     // ---- colour network: rgb head -> delta_c3 -> delta_c2 -> delta_c1 -> dF_s
     HeadBwd hb;
     hb.csave = w.csave; hb.sample_ids = sample_ids; hb.d_rgb = d_rgb; hb.rgb = rgb; hb.wc4 = mlp->wc4; hb.S = S; hb.n_tiles = n_ctiles;
-    hb.slope = slope; hb.d3 = w.dc[2]; hb.dwc4 = gm->wc4; hb.dbc4 = gm->bc4;
+    hb.slope = slope; hb.S_dev = S_dev; hb.d3 = w.dc[2]; hb.dwc4 = gm->wc4; hb.dbc4 = gm->bc4;
     color_head_bwd_kernel<<<n_ctiles < kSMs * 8 ? n_ctiles : kSMs * 8, 128, 0, st>>>(hb);
     PNERF_LAUNCH_CHECK();
     if ((rc = gemm(w.dc[2], CDELTA_TILE_BYTES, 16, w.csave + (int64_t)CSAVE_C2 * SLAB, CSAVE_TILE_BYTES, w.dc[1], CDELTA_TILE_BYTES, nullptr, 0,
-                   WBC3, 128, n_ctiles))) return rc;                                   // delta_c2 = lrelu'(c2) * (delta_c3 Wc3)
+                   WBC3, 128, n_ctiles, ROWS))) return rc;                                   // delta_c2 = lrelu'(c2) * (delta_c3 Wc3)
     if ((rc = gemm(w.dc[1], CDELTA_TILE_BYTES, 16, w.csave + (int64_t)CSAVE_C1 * SLAB, CSAVE_TILE_BYTES, w.dc[0], CDELTA_TILE_BYTES, nullptr, 0,
-                   WBC2, 128, n_ctiles))) return rc;                                   // delta_c1 = lrelu'(c1) * (delta_c2 Wc2)
-    if ((rc = gemm(w.dc[0], CDELTA_TILE_BYTES, 16, nullptr, 0, nullptr, 0, w.dF, HID, WBC1, 256, n_ctiles))) return rc;   // dF_s = delta_c1 Wc1[:, :256]
+                   WBC2, 128, n_ctiles, ROWS))) return rc;                                   // delta_c1 = lrelu'(c1) * (delta_c2 Wc2)
+    if ((rc = gemm(w.dc[0], CDELTA_TILE_BYTES, 16, nullptr, 0, nullptr, 0, w.dF, HID, WBC1, 256, n_ctiles, ROWS))) return rc;   // dF_s = delta_c1 Wc1[:, :256]
     // ---- aggregation + density head backward -> delta_4
     AggBwd a;
     a.save = w.save; a.save_w = w.save_w; a.save_raw = w.save_raw; a.sample_ids = sample_ids; a.d_sigma = d_sigma; a.dF = w.dF; a.ldF = HID;
     a.wa = mlp->wa; a.S = S; a.KP = KP; a.n_tiles = n_tiles; a.softplus = mode->density_softplus; a.slope = slope;
-    a.d4 = w.d[3]; a.dwa = gm->wa; a.dba = gm->ba; a.dw_rows = w.dw_rows;
+    a.S_dev = S_dev; a.d4 = w.d[3]; a.dwa = gm->wa; a.dba = gm->ba; a.dw_rows = w.dw_rows;
     agg_bwd_kernel<<<n_tiles < kSMs * 8 ? n_tiles : kSMs * 8, 128, 0, st>>>(a);
     PNERF_LAUNCH_CHECK();
     // ---- dgrad chain of mlp_head / mlp_base
     auto dgrad = [&](const uint8_t* in, int mask_slab, uint8_t* out_bf, float* out_f32, int64_t wb, int N) -> int {
         return gemm(in, DELTA_TILE_BYTES, 32, mask_slab >= 0 ? w.save + (int64_t)mask_slab * SLAB : nullptr, SAVE_TILE_BYTES, out_bf,
-                    DELTA_TILE_BYTES, out_f32, NX0, wb, N, n_tiles);
+                    DELTA_TILE_BYTES, out_f32, NX0, wb, N, n_tiles, ROWS / KP);
     };
     if ((rc = dgrad(w.d[3], SAVE_H3, w.d[2], nullptr, WB4, 256))) return rc;      // delta_3 = lrelu'(h3) * (delta_4 W4)
     if ((rc = dgrad(w.d[2], SAVE_X3, w.d[1], nullptr, WB3, 256))) return rc;      // delta_2 = lrelu'(h2) * (delta_3 W3[:, :256])
     if ((rc = dgrad(w.d[1], SAVE_H1, w.d[0], nullptr, WB2, 256))) return rc;      // delta_1 = lrelu'(h1) * (delta_2 W2)
     if (g_embed && (rc = dgrad(w.d[0], -1, nullptr, w.dx0, WB1, NX0))) return rc; // d x0[:, :224] = delta_1 W1[:, :224]
+    // ---- point gradients first: they are the large collective of a data-parallel step (156 B per point), which can then start
+    // (on another stream, after `points_done_event`) under the weight-gradient GEMMs below
+    if (g_embed || g_color || g_dir || (g_conf && mode->weight_conf)) {
+        ScatterP s;
+        s.cam = make_cam(pts, cam);
+        s.sample_pidx = sample_pidx; s.sample_ids = sample_ids; s.dirs = dirs; s.embed = pts->embed; s.conf = pts->conf;
+        s.dx0 = w.dx0; s.d3 = w.d[2]; s.w3 = mlp->w3; s.dw_rows = w.dw_rows; s.save_w = w.save_w;
+        s.S = S; s.S_dev = S_dev; s.SR = SR; s.K = K; s.KP = KP; s.n_tiles = n_tiles; s.weight_conf = mode->weight_conf;
+        s.g_embed = g_embed; s.g_color = g_color; s.g_dir = g_dir; s.g_conf = g_conf;
+        scatter_kernel<<<n_tiles < kSMs * 8 ? n_tiles : kSMs * 8, 128, 0, st>>>(s);
+        PNERF_LAUNCH_CHECK();
+    }
+    if (points_done_event) PNERF_CUDA(cudaEventRecord((cudaEvent_t)points_done_event, st));
     // ---- wgrad + bias gradients: one launch each for all seven layers
     {
         WgradP g;
+        g.S_dev = S_dev;
         int nj = 0;
         float* dWf[4] = {gm->w1, gm->w2, gm->w3, gm->w4};
         const int in_dim[4] = {284, 256, 263, 256}, xoff[4] = {SAVE_X0, SAVE_H1, SAVE_X3, SAVE_H3}, xsl[4] = {36, 32, 36, 32};
         for (int L = 0; L < 4; L++)
             for (int h = 0; h < 2; h++)
-                if (dWf[L]) g.j[nj++] = {w.d[L], DELTA_TILE_BYTES, 16 * h, w.save, SAVE_TILE_BYTES, xoff[L], xsl[L], dWf[L], in_dim[L], 128 * h, n_tiles};
+                if (dWf[L]) g.j[nj++] = {w.d[L], DELTA_TILE_BYTES, 16 * h, w.save, SAVE_TILE_BYTES, xoff[L], xsl[L], dWf[L], in_dim[L], 128 * h, n_tiles, ROWS / KP};
         float* dWc[3] = {gm->wc1, gm->wc2, gm->wc3};
         const int cin[3] = {280, 128, 128}, coff[3] = {CSAVE_C0, CSAVE_C1, CSAVE_C2}, csl[3] = {36, 16, 16};
         for (int L = 0; L < 3; L++)
-            if (dWc[L]) g.j[nj++] = {w.dc[L], CDELTA_TILE_BYTES, 0, w.csave, CSAVE_TILE_BYTES, coff[L], csl[L], dWc[L], cin[L], 0, n_ctiles};
+            if (dWc[L]) g.j[nj++] = {w.dc[L], CDELTA_TILE_BYTES, 0, w.csave, CSAVE_TILE_BYTES, coff[L], csl[L], dWc[L], cin[L], 0, n_ctiles, ROWS};
         g.n_jobs = nj;
         if (nj > 0) {
             const size_t wsm = sizeof(WgSmem);
@@ -629,21 +658,11 @@ extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_came
             PNERF_LAUNCH_CHECK();
         }
         ColsumP c;
+        c.S_dev = S_dev;
         float* db[7] = {gm->b1, gm->b2, gm->b3, gm->b4, gm->bc1, gm->bc2, gm->bc3};
-        for (int i = 0; i < 4; i++) c.j[i] = {w.d[i], DELTA_TILE_BYTES, 32, db[i], n_tiles};
-        for (int i = 0; i < 3; i++) c.j[4 + i] = {w.dc[i], CDELTA_TILE_BYTES, 16, db[4 + i], n_ctiles};
+        for (int i = 0; i < 4; i++) c.j[i] = {w.d[i], DELTA_TILE_BYTES, 32, db[i], n_tiles, ROWS / KP};
+        for (int i = 0; i < 3; i++) c.j[4 + i] = {w.dc[i], CDELTA_TILE_BYTES, 16, db[4 + i], n_ctiles, ROWS};
         colsum_kernel<<<dim3(n_tiles < 64 ? n_tiles : 64, 7), 256, 0, st>>>(c);
-        PNERF_LAUNCH_CHECK();
-    }
-    // ---- point gradients
-    if (g_embed || g_color || g_dir || (g_conf && mode->weight_conf)) {
-        ScatterP s;
-        s.cam = make_cam(pts, cam);
-        s.sample_pidx = sample_pidx; s.sample_ids = sample_ids; s.dirs = dirs; s.embed = pts->embed; s.conf = pts->conf;
-        s.dx0 = w.dx0; s.d3 = w.d[2]; s.w3 = mlp->w3; s.dw_rows = w.dw_rows; s.save_w = w.save_w;
-        s.S = S; s.SR = SR; s.K = K; s.KP = KP; s.n_tiles = n_tiles; s.weight_conf = mode->weight_conf;
-        s.g_embed = g_embed; s.g_color = g_color; s.g_dir = g_dir; s.g_conf = g_conf;
-        scatter_kernel<<<n_tiles < kSMs * 8 ? n_tiles : kSMs * 8, 128, 0, st>>>(s);
         PNERF_LAUNCH_CHECK();
     }
     return PNERF_OK;

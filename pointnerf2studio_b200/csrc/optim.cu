@@ -43,10 +43,83 @@ __global__ void __launch_bounds__(256) adam_kernel(Segs segs, float omb1, float 
         sg.p[i] = p; sg.m[i] = m; sg.v[i] = v;
     }
 }
+
+// ---------------------------------------------------------------------------------------------- data-parallel step
+// Gradient reduction + Adam + parameter broadcast of a ray-sharded training step as ONE kernel over peer-mapped memory (NVLink /
+// NVSwitch), instead of NCCL all-reduce followed by a replicated dense Adam (what DDP + torch.optim.Adam do for the reference,
+// studio_pipeline.py:48-53): all parameters and gradients of a rank live in two flat buffers with the same layout on every rank;
+// rank r owns the slice [lo, hi): it reads that slice of EVERY rank's gradient buffer (local + world-1 peer loads), averages,
+// applies Adam with ITS slice of the moments (optimiser state sharded: 1/world of the Adam traffic per GPU) and stores the new
+// parameters into EVERY rank's parameter buffer.  Per GPU and step the links carry (world-1)/world of the flat size in each
+// direction, half of what a ring / tree all-reduce moves, and the dense Adam pass over all N points disappears from 7 of 8 GPUs.
+// The caller brackets the launch with two cross-rank barriers (gradients complete / parameters delivered).
+struct DpArgs {
+    float* p[PNERF_DP_MAX_RANKS];
+    const float* g[PNERF_DP_MAX_RANKS];
+    float *m, *v;
+    int64_t lo, hi, boundary;
+    float lr_c[2], inv_bc2_sqrt;
+    int world, me;
+};
+
+template <int W>
+__global__ void __launch_bounds__(512) dp_adam_kernel(const DpArgs a, float omb1, float b2, float omb2, float eps, float gscale) {
+    const int64_t n4 = (a.hi - a.lo) >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int64_t e = a.lo + 4 * i;
+        float4 gs[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) gs[w] = __ldcs(reinterpret_cast<const float4*>(a.g[w] + e));       // all loads in flight before the first add
+        float4 g = gs[0];
+#pragma unroll
+        for (int w = 1; w < W; w++) { g.x += gs[w].x; g.y += gs[w].y; g.z += gs[w].z; g.w += gs[w].w; }
+        g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale;
+        float4 p = *reinterpret_cast<const float4*>(a.p[a.me] + e);
+        float4 m = reinterpret_cast<float4*>(a.m)[i], v = reinterpret_cast<float4*>(a.v)[i];
+        const float l0 = e + 0 < a.boundary ? a.lr_c[0] : a.lr_c[1], l1 = e + 1 < a.boundary ? a.lr_c[0] : a.lr_c[1];
+        const float l2 = e + 2 < a.boundary ? a.lr_c[0] : a.lr_c[1], l3 = e + 3 < a.boundary ? a.lr_c[0] : a.lr_c[1];
+        adam1(p.x, g.x, m.x, v.x, l0, omb1, b2, omb2, eps, a.inv_bc2_sqrt);
+        adam1(p.y, g.y, m.y, v.y, l1, omb1, b2, omb2, eps, a.inv_bc2_sqrt);
+        adam1(p.z, g.z, m.z, v.z, l2, omb1, b2, omb2, eps, a.inv_bc2_sqrt);
+        adam1(p.w, g.w, m.w, v.w, l3, omb1, b2, omb2, eps, a.inv_bc2_sqrt);
+        reinterpret_cast<float4*>(a.m)[i] = m;
+        reinterpret_cast<float4*>(a.v)[i] = v;
+#pragma unroll
+        for (int w = 0; w < W; w++) *reinterpret_cast<float4*>(a.p[w] + e) = p;
+    }
+}
 }  // namespace
 }  // namespace pnerf
 
 using namespace pnerf;
+
+extern "C" int pnerf_dp_adam_step(const pnerf_dp_adam* h, float beta1, float beta2, float eps, float grad_scale, void* stream) {
+    if (!h || h->world < 1 || h->world > PNERF_DP_MAX_RANKS || h->rank < 0 || h->rank >= h->world || h->step < 1) return PNERF_ERR_ARG;
+    if (h->lo < 0 || h->hi < h->lo || ((h->lo | h->hi) & 3) || !h->m || !h->v) return PNERF_ERR_ARG;
+    if (h->hi == h->lo) return PNERF_OK;
+    DpArgs a;
+    // slot 0 = this rank (local loads first), then the peers starting with the next rank: the ranks' peer traffic is spread over all links
+    for (int i = 0; i < h->world; i++) {
+        const int w = (h->rank + i) % h->world;
+        if (!h->p[w] || !h->g[w] || (((uintptr_t)h->p[w] | (uintptr_t)h->g[w]) & 15)) return PNERF_ERR_ARG;
+        a.p[i] = h->p[w]; a.g[i] = h->g[w];
+    }
+    a.me = 0;
+    a.m = h->m; a.v = h->v; a.lo = h->lo; a.hi = h->hi; a.boundary = h->boundary; a.world = h->world;
+    const double bc1 = 1.0 - pow((double)beta1, (double)h->step), bc2 = 1.0 - pow((double)beta2, (double)h->step);
+    a.lr_c[0] = (float)(h->lr[0] / bc1); a.lr_c[1] = (float)(h->lr[1] / bc1); a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+    const int64_t n4 = (h->hi - h->lo) >> 2;
+    int64_t blocks = (n4 + 511) / 512;
+    blocks = blocks < 1 ? 1 : (blocks > (int64_t)kSMs * 4 ? (int64_t)kSMs * 4 : blocks);
+    const float omb1 = (float)(1.0 - (double)beta1), omb2 = (float)(1.0 - (double)beta2);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PNERF_DP(W) case W: dp_adam_kernel<W><<<(unsigned)blocks, 512, 0, st>>>(a, omb1, beta2, omb2, eps, grad_scale); break
+    switch (h->world) { PNERF_DP(1); PNERF_DP(2); PNERF_DP(3); PNERF_DP(4); PNERF_DP(5); PNERF_DP(6); PNERF_DP(7); PNERF_DP(8); default: return PNERF_ERR_ARG; }
+#undef PNERF_DP
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
 
 extern "C" int pnerf_adam_step(const pnerf_adam_seg* segs_h, int n_segs, float beta1, float beta2, float eps, float grad_scale,
                                void* stream) {

@@ -23,7 +23,7 @@ import torch
 from torch import nn
 from torch.nn import Parameter
 
-from . import native
+from . import native, ops  # noqa: F401  (ops registers the pnerf:: custom ops)
 
 
 HIT_COMPACTION_MIN_RAYS = 32768       # bundles up to this size skip the hit-ray compaction (R -> R')
@@ -338,16 +338,31 @@ class NeuralPoints(nn.Module):
 
 
 class ConfCoefficient:
-    """What `outputs["conf_coefficient"]` carries in training (SM:396-397).  The reference stores the
-    gathered (1,R'',SR,K) tensor; here it is a handle so the loss kernel can read the indices directly."""
+    """What `outputs["conf_coefficient"]` carries in training (SM:396-397): the straight-through-clamped confidences gathered at
+    all (1,R'',SR,K) slots.  The loss kernel reads the indices directly, so the gathered tensor is only built when somebody asks
+    for it: the object behaves as that tensor in any torch function (`torch.clamp(cc, ...)`, `torch.log(cc)`, `cc.shape`, ...) and
+    materialises it on first use (one boolean-mask gather, i.e. one host sync, exactly what SU:194-203 costs the reference)."""
 
     def __init__(self, conf, pidx, ray_mask, n_rays):
         self.conf, self.pidx, self.ray_mask, self.n_rays = conf, pidx, ray_mask, n_rays
+        self._t = None
 
     def materialize(self):
-        keep = self.ray_mask.bool()
-        c = self.conf.reshape(-1)[self.pidx[keep].clamp(min=0).long()]
-        return (c - (c - c.clamp(1e-4, 1)).detach())[None]
+        if self._t is None:
+            keep = self.ray_mask.bool()
+            c = self.conf.reshape(-1)[self.pidx[keep].clamp(min=0).long()]
+            self._t = (c - (c - c.clamp(1e-4, 1)).detach())[None]
+        return self._t
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        unwrap = lambda a: a.materialize() if isinstance(a, ConfCoefficient) else a
+        return func(*[unwrap(a) for a in args], **{k: unwrap(v) for k, v in (kwargs or {}).items()})
+
+    def __getattr__(self, name):          # .shape, .clamp(...), .detach(), ... of the gathered tensor
+        if name.startswith("__") or name in ("conf", "pidx", "ray_mask", "n_rays", "_t"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
 
 
 class PointNerf(nn.Module):
@@ -430,9 +445,51 @@ class PointNerf(nn.Module):
         finally:
             native.unpin_stream()
 
+    def set_grad_sink(self, sink_points=None, sink_mlp=None, points_done_event=0):
+        """A data-parallel trainer (parallel.TrainEngine) hands the backward kernels the flat buffers the gradients are to be
+        accumulated in (`.grad` of the parameters aliases them) and, optionally, a CUDA event to record as soon as the point
+        gradients are complete.  None / 0 restores plain autograd behaviour (fresh gradient tensors per call)."""
+        self._grad_sink = (sink_points, sink_mlp, int(points_done_event))
+
+    def _get_outputs_train_fused(self, ray_bundle, generator=None):
+        """Training step forward on the tensor-core path as ONE custom op (`pnerf::render_train`): selection, query, compaction,
+        field networks, compositing and ray mask in one host call, nothing read back from the device."""
+        from . import native_tc, ops
+        c, npnts = self.config, self.neural_points
+        origin, R_c2w, near, far = npnts.camera_of(ray_bundle, with_near_far=True)
+        dirs = ray_bundle.directions.to(self._device).float().contiguous()
+        R = dirs.shape[0]
+        grid = npnts.grid()
+        t_vals, t_stride, seed, jitter = None, 0, 0, float(c.jitter)
+        if jitter and generator is None:
+            npnts._jitter_calls += 1
+            seed = (int(c.jitter_seed) << 32) | (npnts._jitter_calls & 0xffffffff)
+            npnts._last_jitter = (near, far, jitter, seed)
+        else:                          # an explicit generator or jitter 0: the torch t table (SU:166 semantics, replayable)
+            t_vals = npnts.coarse_t(R, near, far, jitter, generator)
+            t_stride = 0 if t_vals.dim() == 1 else c.z_depth_dim
+        mode = native.make_mode(c.flow, training=self.training, bg=self._background_color.tolist(), vsize_z=c.vsize[2])
+        params = self.mlp_param_list()
+        wpack = native_tc.packed_weights(params)[0]
+        sink_points, sink_mlp, event = self.__dict__.get("_grad_sink", (None, None, 0))
+        fl, it = ops.fl_it(grid.frame, origin, R_c2w, native._rw2c_host(npnts.points_Rw2c), near, far, jitter, float(npnts.radius_limit_np),
+                           mode, c.z_depth_dim, c.SR, c.K, int(npnts.kernel_size[0]), seed=seed, t_stride=t_stride, event=event)
+        (rgb, ray_mask, n_rays, pidx, loc, valid, cnt, sigma, srgb, ids, n_samples, _ws, _ridx) = torch.ops.pnerf.render_train(
+            dirs, npnts.points_xyz, npnts.points_embeding.view(-1, c.point_features_dim), npnts.points_color.view(-1, 3),
+            npnts.points_dir.view(-1, 3), npnts.points_conf.view(-1, 1), [p for p in params], wpack, grid.cell_start, grid.recs,
+            grid.occ_bits, t_vals, sink_points, sink_mlp, fl, it)
+        out = {"coarse_raycolor": rgb, "ray_mask": ray_mask,
+               "conf_coefficient": ConfCoefficient(npnts.points_conf, pidx, ray_mask, n_rays)}
+        self._last_query = native.QueryResult(loc, cnt, pidx, valid)
+        self._last_render = {"sigma": sigma, "rgb": srgb, "n_samples": n_samples}
+        return out
+
     def _get_outputs(self, ray_bundle, generator=None):
         c = self.config
         npnts = self.neural_points
+        if (c.precision == "bf16" and self.training and torch.is_grad_enabled() and 0 < len(ray_bundle) <= HIT_COMPACTION_MIN_RAYS
+                and any(p.requires_grad for p in self.parameters())):
+            return self._get_outputs_train_fused(ray_bundle, generator)
         # dropping the rays without an occupied position (R -> R') costs a host sync and six small launches: worth it for an image,
         # not for a 4096-ray training batch, where those rays are nearly free in every kernel anyway
         q, origin, R_c2w, dirs = npnts.query(ray_bundle, generator=generator, compact=len(ray_bundle) > HIT_COMPACTION_MIN_RAYS)
@@ -559,13 +616,15 @@ class PointNerf(nn.Module):
             image = image.to(device=pred.device, dtype=pred.dtype)
         mask = outputs["ray_mask"]
         if pred.shape[0] > 0:      # MSELoss over the masked_select rows + 1e-6, one kernel each way
-            loss_dict = {"ray_masked_coarse_raycolor_loss": native.masked_mse(pred, image, mask.to(torch.int8).contiguous())}
+            mask8 = mask if (mask.dtype == torch.int8 and mask.is_contiguous()) else mask.to(torch.int8).contiguous()
+            loss_dict = {"ray_masked_coarse_raycolor_loss": torch.ops.pnerf.masked_mse(pred, image.contiguous(), mask8)[0]}
         else:
             loss_dict = {"ray_masked_coarse_raycolor_loss": pred.sum() * float("nan")}      # empty bundle: MSELoss of nothing
         if self.training and "conf_coefficient" in outputs:
             h = outputs["conf_coefficient"]
-            loss_dict["conf_coefficient_loss"] = native.conf_loss(h.conf.view(-1, 1), h.pidx, h.ray_mask, h.n_rays,
-                                                                  self.config.zero_epsilon, self.config.zero_one_loss_weights)
+            loss_dict["conf_coefficient_loss"] = torch.ops.pnerf.conf_loss(h.conf.view(-1, 1), h.pidx, h.ray_mask, h.n_rays,
+                                                                           float(self.config.zero_epsilon),
+                                                                           float(self.config.zero_one_loss_weights))[0]
         for k, v in self.config.loss_coefficients.items():                  # misc.scale_dict (SM:430)
             if k in loss_dict:
                 loss_dict[k] = loss_dict[k] * v

@@ -75,7 +75,7 @@ class _RenderTC(torch.autograd.Function):
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         with Timers.span("field"):
             check(lib.pnerf_field_forward_tc_train(C.byref(pts), C.byref(cfg["camera"]), C.byref(mlp), _ptr(wpack), C.byref(cfg["mode"]),
-                                                   _ptr(dirs), _ptr(q.sample_loc), _ptr(q.sample_pidx), _ptr(ids), S, SR, K,
+                                                   _ptr(dirs), _ptr(q.sample_loc), _ptr(q.sample_pidx), _ptr(ids), S, None, SR, K,
                                                    _ptr(sigma), _ptr(rgb), _ptr(ws), ws_bytes, _stream()), "pnerf_field_forward_tc_train")
         LAUNCHES["n"] += 7
         out = native.composite_forward(cfg, q, sigma, rgb)
@@ -122,8 +122,8 @@ class _RenderTC(torch.autograd.Function):
         gm = make_mlp(grads, _lib.MlpGrad)
         with Timers.span("field_bwd"):
             check(lib.pnerf_field_backward_tc(C.byref(pts), C.byref(cam), C.byref(mlp), C.byref(mode), _ptr(dirs), _ptr(q.sample_loc),
-                                              _ptr(q.sample_pidx), _ptr(ids), S, SR, K, _ptr(d_sigma), _ptr(d_rgb), _ptr(rgb), _ptr(g_embed),
-                                              _ptr(g_color), _ptr(g_dir), _ptr(g_conf), C.byref(gm), _ptr(ws), ws.numel(), _stream()),
+                                              _ptr(q.sample_pidx), _ptr(ids), S, None, SR, K, _ptr(d_sigma), _ptr(d_rgb), _ptr(rgb), _ptr(g_embed),
+                                              _ptr(g_color), _ptr(g_dir), _ptr(g_conf), C.byref(gm), _ptr(ws), ws.numel(), None, _stream()),
                   "pnerf_field_backward_tc")
         LAUNCHES["n"] += 22
         mlp_grads = [grads[n].reshape(s) for n, s in zip(names, ctx.shapes)]

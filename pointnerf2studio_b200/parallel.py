@@ -156,3 +156,150 @@ class SharedHostImage:
                 os.unlink(self.path)
             except OSError:
                 pass
+
+
+class TrainEngine:
+    """One training step of the plugin on N ranks: forward -> losses -> backward -> gradient exchange -> Adam on both parameter
+    groups (studio_config.py:33-48) with the reference's exponential decay (studio_utils.py:38-44).
+
+    All trainable parameters of a rank live in ONE flat fp32 buffer P = [embedding N*32 | colour N*3 | dir N*3 | conf N | the 18
+    MLP tensors] (the module's Parameters become views of it, names and shapes unchanged) and all gradients in a second flat
+    buffer G with the same layout (`.grad` of every Parameter is a view of G; the backward kernels accumulate straight into it
+    through PointNerf.set_grad_sink, so no gradient is ever copied, concatenated or re-allocated).  Gradient exchange:
+
+      "p2p"   (default at world > 1 when torch's symmetric memory is available): P and G are peer-mapped on every rank and ONE
+              kernel (pnerf_dp_adam_step) does reduce-scatter + Adam + all-gather over NVLink between two device-side barriers;
+              the Adam moments are sharded (rank r keeps them for its 1/world slice only).
+      "nccl"  one in-place NCCL all-reduce per bucket -- the point gradients start on a side stream as soon as the backward has
+              scattered them (under the weight-gradient GEMMs), the confidence + MLP bucket follows -- then the same fused Adam
+              kernel runs replicated on every rank.  This is DDP's data movement.
+      "local" world == 1.
+    """
+
+    def __init__(self, model, dist=None, exchange: str = "auto", lr_fields: float = 5e-4, lr_points: float = 2e-3,
+                 lr_decay_exp: float = 0.1, lr_decay_iters: int = 1000000, betas=(0.9, 0.999), eps: float = 1e-8):
+        from . import _lib
+        self.model, self.dist = model, dist
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.lr0 = (float(lr_points), float(lr_fields))
+        self.decay = (float(lr_decay_exp), float(lr_decay_iters))
+        self.betas, self.eps, self.steps = betas, float(eps), 0
+        self.timing = None           # set to a list to collect (start, end) CUDA-event pairs around update()
+        self._lib = _lib.load()
+        npnts = model.neural_points
+        dev = npnts.points_xyz.device
+        N = npnts.points_xyz.shape[0]
+        pts = [npnts.points_embeding, npnts.points_color, npnts.points_dir, npnts.points_conf]
+        mlp = model.mlp_param_list()
+        assert [p.numel() for p in pts] == [N * 32, N * 3, N * 3, N]
+        self.N, self.boundary = N, N * 39
+        self.total = self.boundary + sum(p.numel() for p in mlp)
+        W = self.world
+        self.slice = (self.total + 4 * W - 1) // (4 * W) * 4
+        padded = self.slice * W
+        if exchange == "auto":
+            exchange = "local" if W == 1 else ("p2p" if self._symm_ok() else "nccl")
+        self.exchange = exchange
+        self._hdl_p = self._hdl_g = None
+        if exchange == "p2p":
+            import torch.distributed._symmetric_memory as symm_mem
+            group = dist.group.WORLD.group_name
+            self.P = symm_mem.empty(padded, dtype=torch.float32, device=dev)
+            self.G = symm_mem.empty(padded, dtype=torch.float32, device=dev)
+            self._hdl_p, self._hdl_g = symm_mem.rendezvous(self.P, group), symm_mem.rendezvous(self.G, group)
+            self.P.zero_()
+        else:
+            self.P = torch.zeros(padded, dtype=torch.float32, device=dev)
+            self.G = torch.empty(padded, dtype=torch.float32, device=dev)
+        self.G.zero_()
+        self.params = pts + mlp
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                view = self.P[off:off + n].view(p.shape)
+                view.copy_(p.detach())
+                p.data = view                     # same Parameter object (optimiser / checkpoint code keeps working), storage in P
+                if p.requires_grad:
+                    p.grad = self.G[off:off + n].view(p.shape)
+                off += n
+        assert off == self.total
+        lo = self.rank * self.slice if exchange == "p2p" else 0
+        hi = min(lo + self.slice, padded) if exchange == "p2p" else padded
+        self.lo, self.hi = lo, hi
+        self.m = torch.zeros(hi - lo, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(hi - lo, dtype=torch.float32, device=dev)
+        self._ev = torch.cuda.Event()
+        self._comm = torch.cuda.Stream(device=dev) if exchange == "nccl" else None
+        self._ev.record()
+        model.set_grad_sink(self.G[:self.boundary], self.G[self.boundary:self.total], self._ev.cuda_event if exchange == "nccl" else 0)
+        if exchange == "p2p":
+            self._hdl_p.barrier()
+
+    def _symm_ok(self) -> bool:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+            return self.dist.get_backend() == "nccl"
+        except Exception:
+            return False
+
+    def lrs(self):
+        """LambdaLR semantics: optimiser step k (1-based) runs with lr0 * lambda(k - 1)."""
+        f = pow(self.decay[0], self.steps / self.decay[1])
+        return self.lr0[0] * f, self.lr0[1] * f
+
+    def backward_and_update(self, loss: torch.Tensor):
+        loss.backward()
+        self.update()
+
+    def update(self):
+        """Gradient exchange + Adam + gradient reset, all enqueued on the current stream (nothing blocks the host)."""
+        import ctypes as C
+        from . import _lib
+        lr_p, lr_f = self.lrs()
+        self.steps += 1
+        if self.timing is not None:
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+        a = _lib.DpAdam()
+        W = self.world
+        if self.exchange == "p2p":
+            for w in range(W):
+                a.p[w], a.g[w] = self._hdl_p.buffer_ptrs[w], self._hdl_g.buffer_ptrs[w]
+            a.world, a.rank = W, self.rank
+            self._hdl_g.barrier()                     # every rank's gradients are complete
+        else:
+            if self.exchange == "nccl":
+                cur = torch.cuda.current_stream()
+                n_early = self.N * 38                  # embedding / colour / dir: complete at the event recorded inside the backward
+                with torch.cuda.stream(self._comm):
+                    self._comm.wait_event(self._ev)
+                    w1 = self.dist.all_reduce(self.G[:n_early], async_op=True)
+                w2 = self.dist.all_reduce(self.G[n_early:self.total], async_op=True)
+                w1.wait(); w2.wait()
+                cur.wait_stream(self._comm)
+            a.p[0], a.g[0] = self.P.data_ptr(), self.G.data_ptr()
+            a.world, a.rank = 1, 0
+        a.m, a.v = self.m.data_ptr(), self.v.data_ptr()
+        a.lo, a.hi, a.boundary, a.step = self.lo, self.hi, self.boundary, self.steps
+        a.lr = (C.c_float * 2)(lr_p, lr_f)
+        _lib.check(self._lib.pnerf_dp_adam_step(C.byref(a), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                                                C.c_float(1.0 / W), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pnerf_dp_adam_step")
+        if self.exchange == "p2p":
+            self._hdl_p.barrier()                     # every rank has read my gradients and written my parameters
+        self.G.zero_()
+        from . import native
+        native.LAUNCHES["n"] += 2
+        torch.autograd.graph.increment_version(self.params)
+        if self.timing is not None:
+            t1.record()
+            self.timing.append((t0, t1))
+
+    def step(self, ray_bundle, image):
+        """-> the (rank-local) loss tensor; nothing is read back."""
+        out = self.model.get_outputs(ray_bundle)
+        loss_dict = self.model.get_loss_dict(out, {"image": image})
+        loss = sum(loss_dict.values())
+        self.backward_and_update(loss)
+        return loss
