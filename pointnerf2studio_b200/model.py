@@ -25,6 +25,17 @@ from torch.nn import Parameter
 
 from . import native, ops  # noqa: F401  (ops registers the pnerf:: custom ops)
 
+try:      # Nerfstudio (>= 0.3, the reference's only framework dependency) is optional: subclass its Model / ModelConfig when it is there
+    from nerfstudio.models.base_model import Model as _ModelBase, ModelConfig as _ConfigBase
+    HAVE_NERFSTUDIO = True
+except Exception:
+    HAVE_NERFSTUDIO = False
+    _ModelBase = nn.Module
+
+    @dataclass
+    class _ConfigBase:
+        pass
+
 
 HIT_COMPACTION_MIN_RAYS = 32768       # bundles up to this size skip the hit-ray compaction (R -> R')
 RENDER_RAYS_PER_LAUNCH = 1 << 21   # rays per query launch in full-image rendering (memory knob only)
@@ -58,10 +69,28 @@ class RayBundle:
                              "camera_host": {"origin": o, "camrotc2w": r, "near": float(near), "far": float(far)}})
 
 
+class NearFarCollider(nn.Module):
+    """What nerfstudio's NearFarCollider does for the reference (Model.populate_modules, called at SM:171): every ray gets the
+    two planes of `collider_params`.  Used only when Nerfstudio is absent; a bundle that already carries nears / fars keeps them."""
+
+    def __init__(self, near_plane: float, far_plane: float):
+        super().__init__()
+        self.near_plane, self.far_plane = float(near_plane), float(far_plane)
+
+    def forward(self, ray_bundle):
+        if getattr(ray_bundle, "nears", None) is None or getattr(ray_bundle, "fars", None) is None:
+            ones = torch.ones_like(ray_bundle.origins[..., 0:1])
+            ray_bundle.nears, ray_bundle.fars = ones * self.near_plane, ones * self.far_plane
+        return ray_bundle
+
+
 @dataclass
-class PointNerfConfig:
-    """Every field of the reference's PointNerfConfig (SM:61-118), same names and defaults."""
+class PointNerfConfig(_ConfigBase):
+    """Every field of the reference's PointNerfConfig (SM:61-118), same names and defaults (a nerfstudio ModelConfig when
+    Nerfstudio is importable)."""
     _target: Any = dataclasses.field(default_factory=lambda: PointNerf)
+    enable_collider: bool = True                  # ModelConfig defaults the reference inherits: NearFarCollider(2.0, 6.0)
+    collider_params: Optional[Dict[str, float]] = dataclasses.field(default_factory=lambda: {"near_plane": 2.0, "far_plane": 6.0})
     path_point_cloud: Optional[Path] = None
     eval_num_rays_per_chunk: int = 4096
     feat_grad: bool = True
@@ -365,17 +394,26 @@ class ConfCoefficient:
         return getattr(self.materialize(), name)
 
 
-class PointNerf(nn.Module):
-    """SM:122-504.  `get_outputs(ray_bundle)` -> {"coarse_raycolor" (R,3), "ray_mask" (R,) int8,
-    ["conf_coefficient"]}; `get_param_groups()` -> {"fields", "neural_points"}; `get_loss_dict`."""
+class PointNerf(_ModelBase):
+    """SM:122-504 -- a nerfstudio `Model` when Nerfstudio is importable, otherwise an nn.Module with the same method set.
+    `get_outputs(ray_bundle)` -> {"coarse_raycolor" (R,3), "ray_mask" (R,) int8, ["conf_coefficient"]};
+    `get_param_groups()` -> {"fields", "neural_points"}; `get_loss_dict`; `get_outputs_for_camera_ray_bundle`;
+    `get_image_metrics_and_images`; `get_metrics_dict`; `get_training_callbacks`."""
+    config: PointNerfConfig
 
-    def __init__(self, config: PointNerfConfig, cameras=None, state_dict=None, device="cuda", **kwargs):
-        super().__init__()
-        self.config = config
+    def __init__(self, config: PointNerfConfig, scene_box=None, num_train_data: int = 0, cameras=None, state_dict=None,
+                 device="cuda", **kwargs):
+        if HAVE_NERFSTUDIO:
+            super().__init__(config=config, scene_box=scene_box, num_train_data=num_train_data, **kwargs)   # calls populate_modules()
+        else:
+            nn.Module.__init__(self)
+            self.config, self.scene_box, self.num_train_data, self.kwargs = config, scene_box, num_train_data, kwargs
+            self.render_aabb, self.collider, self.callbacks = None, None, None
+            self.populate_modules()
+        self._point_initialized = False
         self.cameras = cameras
         self._device = torch.device(device)
         self._init_pointnerf(state_dict)
-        self.populate_modules()
         self.to(self._device)
 
     @property
@@ -391,11 +429,24 @@ class PointNerf(nn.Module):
             state_dict = load_point_cloud_checkpoint(self.config.path_point_cloud)
         self._loaded_state = state_dict
         self.neural_points = NeuralPoints(state_dict, self._device, self.config)
+        from .checkpoint import AGGREGATOR_MAP
+        if any(k.startswith("aggregator.") for k in state_dict):     # original-flow checkpoint: reuse its MLPs
+            own = dict(self.named_parameters())
+            with torch.no_grad():
+                for new, old in AGGREGATOR_MAP.items():
+                    for s in ("weight", "bias"):
+                        own[f"{new}.{s}"].copy_(state_dict[f"aggregator.{old}.{s}"])
         self._point_initialized = True
 
     def populate_modules(self):
-        """SM:169-237 (networks only; metrics are image-quality evaluation, out of scope)."""
+        """SM:169-237: collider (through the base class, SM:171), encodings, networks, background.  The image-quality metric
+        modules (PSNR / SSIM / LPIPS objects, SM:229-236) are evaluation tooling outside the hot path: get_image_metrics_and_images
+        computes PSNR / RMSE directly and adds SSIM / LPIPS when torchmetrics is importable."""
         c = self.config
+        if HAVE_NERFSTUDIO:
+            super().populate_modules()
+        elif c.enable_collider and c.collider_params is not None:
+            self.collider = NearFarCollider(c.collider_params["near_plane"], c.collider_params["far_plane"])
         self.direction_encoding = PointNeRFEncoding(2, c.num_viewdir_freqs, ori=True)
         self.feature_encoding = PointNeRFEncoding(2, c.num_feat_freqs, ori=False)
         self.dists_encoding = PointNeRFEncoding(2, c.num_dist_freqs, ori=False)
@@ -408,13 +459,19 @@ class PointNerf(nn.Module):
         self.field_output_color = FieldHead(self.mlp_color.get_out_dim(), 3)
         self.field_output_density = FieldHead(self.mlp_head.get_out_dim(), 1)
         self._background_color = torch.ones(3)
-        from .checkpoint import AGGREGATOR_MAP
-        if any(k.startswith("aggregator.") for k in self._loaded_state):     # original-flow checkpoint: reuse its MLPs
-            own = dict(self.named_parameters())
-            with torch.no_grad():
-                for new, old in AGGREGATOR_MAP.items():
-                    for s in ("weight", "bias"):
-                        own[f"{new}.{s}"].copy_(self._loaded_state[f"aggregator.{old}.{s}"])
+
+    def get_background_color(self):
+        """SM:257-261."""
+        return self._background_color
+
+    def get_training_callbacks(self, training_callback_attributes=None):
+        return []
+
+    def get_metrics_dict(self, outputs, batch):
+        return {}            # the reference does not override Model.get_metrics_dict
+
+    def update_to_step(self, step: int) -> None:
+        pass
 
     def mlp_param_list(self):
         """The 14 MLP tensors in the kernels' order; the Parameter objects live as long as the module, so the walk over
@@ -435,6 +492,9 @@ class PointNerf(nn.Module):
                 "fields": [p for n, p in named if not n.startswith("neural_points.points")]}
 
     def forward(self, ray_bundle):
+        """nerfstudio Model.forward: the collider fills nears / fars, then get_outputs."""
+        if self.collider is not None:
+            ray_bundle = self.collider(ray_bundle)
         return self.get_outputs(ray_bundle)
 
     def get_outputs(self, ray_bundle, generator=None):
@@ -594,8 +654,16 @@ class PointNerf(nn.Module):
         """nerfstudio Model.get_outputs_for_camera_ray_bundle.  The reference slices the image into
         eval_num_rays_per_chunk = 2304 rays (SC:25) and rebuilds its grid for each slice; chunking does not change
         any pixel (rays are independent), so here `chunk` only bounds the rays per query launch (default: the whole
-        image) and the field kernels walk the compact list of valid samples in fixed-size pieces."""
+        image) and the field kernels walk the compact list of valid samples in fixed-size pieces.
+        An image-shaped bundle (origins (H,W,3), what Nerfstudio's eval loop passes) gives (H,W,.) outputs; a flat one (R,.)."""
         chunk = chunk or RENDER_RAYS_PER_LAUNCH
+        shape = tuple(ray_bundle.origins.shape[:-1])
+        if len(shape) != 1:          # flatten row-major, metadata included (Model.get_row_major_sliced_ray_bundle upstream)
+            flat = lambda t: t.reshape(-1, t.shape[-1]) if (torch.is_tensor(t) and tuple(t.shape[:len(shape)]) == shape) else t
+            md = {k: flat(v) for k, v in ray_bundle.metadata.items()}
+            ray_bundle = RayBundle(flat(ray_bundle.origins), flat(ray_bundle.directions), flat(ray_bundle.nears), flat(ray_bundle.fars), md)
+        if self.collider is not None:
+            ray_bundle = self.collider(ray_bundle)
         R = len(ray_bundle)
         cols, masks = [], []
         for i in range(0, R, chunk):
@@ -604,9 +672,25 @@ class PointNerf(nn.Module):
             o = self.get_outputs(rb)
             cols.append(o["coarse_raycolor"])
             masks.append(o["ray_mask"])
-        if len(cols) == 1:
-            return {"coarse_raycolor": cols[0], "ray_mask": masks[0]}
-        return {"coarse_raycolor": torch.cat(cols), "ray_mask": torch.cat(masks)}
+        out = {"coarse_raycolor": cols[0] if len(cols) == 1 else torch.cat(cols), "ray_mask": masks[0] if len(masks) == 1 else torch.cat(masks)}
+        if len(shape) != 1:
+            out = {k: v.view(*shape, -1) for k, v in out.items()}
+        return out
+
+    def get_image_metrics_and_images(self, outputs, batch):
+        """SM:433-464: metrics of a full evaluation image + the side-by-side picture.  PSNR and RMSE are computed here; SSIM / LPIPS
+        need torchmetrics (+ network weights), which the reference imports at module level and this build image lacks."""
+        image = batch["image"].to(outputs["coarse_raycolor"].device)
+        rgb = outputs["coarse_raycolor"].reshape(image.shape)
+        combined = torch.cat([image, rgb], dim=1)
+        mse = float(torch.mean((image - rgb) ** 2))
+        metrics = {"psnr": float(10.0 * np.log10(1.0 / max(mse, 1e-20))), "rmse": float(np.sqrt(mse))}
+        try:
+            from torchmetrics.functional.image import structural_similarity_index_measure as ssim
+            metrics["torchmetrics_ssim"] = float(ssim(torch.moveaxis(image, -1, 0)[None], torch.moveaxis(rgb, -1, 0)[None]))
+        except Exception:
+            pass
+        return metrics, {"img": combined}
 
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, torch.Tensor]:
         """SM:415-431: MSE over the masked rays + 1e-6 and, in training, the zero-one confidence term."""

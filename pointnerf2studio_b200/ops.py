@@ -182,7 +182,7 @@ def _render_train_backward(ctx, d_out, *unused):
     R, SR, K = dirs.shape[0], it[IT_SR], it[IT_K]
     n_in = 16
     if d_out is None or R == 0:
-        return (None,) * n_in
+        return (None,) * 6 + ([None] * len(MLP_NUMEL),) + (None,) * (n_in - 7)
     dev = dirs.device
     N = xyz.shape[0]
     need = ctx.needs_input_grad      # per input; a list of flags for the List[Tensor] input
@@ -227,7 +227,7 @@ def _render_train_backward(ctx, d_out, *unused):
                                               _p(g_embed), _p(g_color), _p(g_dir), _p(g_conf), C.byref(gm), ev, _stream()),
               "pnerf_render_train_backward")
     native.LAUNCHES["n"] += 18
-    mlp_ret = None if sink_mlp is not None else views
+    mlp_ret = [None] * len(MLP_NUMEL) if sink_mlp is not None else views
     return (None, None, *ret_pts, mlp_ret, None, None, None, None, None, None, None, None, None)
 
 
