@@ -277,6 +277,27 @@ int pnerf_probe(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pner
                 const uint8_t* sample_valid, const float* sigma, const int* sample_pidx, int R, int SR, int K, float* max_opacity,
                 float* max_loc, float* far_dist, float* avg_color, float* avg_dir, float* avg_conf, float* avg_embed, void* stream);
 
+/* Which probed rays become new neural points (the tensor code of probe_hole, run/train_studio.py:414-423 with
+ * bloat_inds :447-455): over the H x W maps a probe pass produced (pnerf_probe outputs scattered to pixels),
+ *   keep[p] = ray_mask[p] > 0  and  opacity[p] > opacity_thresh  and
+ *             ( some pixel q of p's 3x3 window, clipped to the image, has edge_mask[q] and ray_mask[q] < 1 and |gt[q] - bg| > 0.002
+ *               or (far_thresh > 0 and far_dist[p] > far_thresh and |gt[p] - color[p]| < 0.1) ).
+ * edge_mask may be NULL (every pixel belongs to the frame); color / far_dist may be NULL when far_thresh <= 0.  bg_h: 3 host floats. */
+int pnerf_probe_filter(const int8_t* ray_mask, const float* gt, const float* color, const float* far_dist, const float* opacity,
+                       const uint8_t* edge_mask, const float* bg_h, int H, int W, float far_thresh, float opacity_thresh,
+                       uint8_t* keep, void* stream);
+
+/* Neural-point initialisation, voxel down-sample (construct_vox_points_closest, models/mvs/mvs_utils.py:537-561,
+ * called from run/gen_pnts.py): voxel of a point = floor((xyz - space_min) / vox_size) (fp32); for every occupied voxel, in
+ * (x, y, z) lexicographic order (torch.unique's), its centroid (mean of its points), its integer coordinates and the index of the
+ * point closest to the centroid (lowest index on ties, scatter_min's first-minimum rule).  dim_h: voxels per axis; points outside
+ * [0, dim) are counted in n_outside and ignored.  Outputs hold at most max_out voxels (n_out[0] = the true count).
+ * workspace: pnerf_vox_closest_workspace_bytes(dim_h) bytes (a dense counting grid: 40 B per voxel of the frame). */
+int64_t pnerf_vox_closest_workspace_bytes(const int* dim_h);
+int pnerf_vox_closest(const float* xyz, int64_t n, const float* space_min_h, const float* vox_size_h, const int* dim_h, int max_out,
+                      float* centroid, int* grid_idx, int* min_idx, int* n_out, int* n_outside, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
 /* Masked-ray MSE of get_loss_dict (studio_model.py:415-426): loss_out[0] = sum_{ray_mask > 0} |pred - image|^2 / (3 * #masked) + 1e-6.
  * acc: 3 floats of workspace, ZERO on entry, kept for the backward call (acc[1] = #masked rays).
  * backward: g_pred (R,3) = d_loss[0] * 2 (pred - image) / (3 * #masked) on masked rays, 0 elsewhere; d_loss is a device scalar. */
