@@ -168,6 +168,9 @@ def _render_train_setup(ctx, inputs, output):
     ctx.save_for_backward(dirs, xyz, embed, color, dirn, conf, *mlp, sample_pidx, sample_loc, sample_valid, sample_ids, n_samples, sigma, rgb, ws)
     ctx.fl, ctx.it = list(fl), list(it)
     ctx.sinks = (sink_points, sink_mlp)
+    # autograd must NOT materialise zero gradients for the outputs nobody differentiates: one of them is the multi-GB workspace
+    # (a zeros_like of it costs 4 ms per step), the others are index tensors
+    ctx.set_materialize_grads(False)
     ctx.mark_non_differentiable(ray_mask, n_rays, sample_pidx, sample_loc, sample_valid, sample_cnt, sigma, rgb, sample_ids, n_samples, ws, ray_index)
 
 
@@ -257,9 +260,12 @@ def _mse_setup(ctx, inputs, output):
     pred, image, ray_mask = inputs
     ctx.save_for_backward(pred, image, ray_mask, output[1])
     ctx.mark_non_differentiable(output[1])
+    ctx.set_materialize_grads(False)
 
 
 def _mse_backward(ctx, d_loss, _d_acc):
+    if d_loss is None:
+        return None, None, None
     pred, image, ray_mask, acc = ctx.saved_tensors
     return torch.ops.pnerf.masked_mse_backward(pred, image, ray_mask, acc, d_loss), None, None
 
@@ -305,9 +311,12 @@ def _(conf, sample_pidx, ray_mask, n_rays, eps, weight):
 def _conf_setup(ctx, inputs, output):
     ctx.save_for_backward(output[1])
     ctx.mark_non_differentiable(output[1])
+    ctx.set_materialize_grads(False)
 
 
 def _conf_backward(ctx, d_loss, _d_g):
+    if d_loss is None:
+        return None, None, None, None, None, None
     (g,) = ctx.saved_tensors
     return g * d_loss, None, None, None, None, None
 

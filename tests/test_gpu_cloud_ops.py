@@ -81,13 +81,13 @@ def test_probe_hole_feeds_grow_points():
     s, cloud, cam, _ = _scene("config1")
     model = _make_model(cloud, "bf16", "original", SR=s["SR"], K=s["K"], P=s["P"]).eval()
     with torch.no_grad():       # make the surface opaque so that the densest sample passes the opacity threshold
-        model.field_output_density.net.bias.fill_(60.0)
+        model.field_output_density.net.bias.fill_(400.0)
     H = W = 96
-    small = make_camera(H=H, W=W, focal=cam.focal * H / cam.H * 2.2)
+    small = make_camera(H=H, W=W, focal=cam.focal * H / cam.H * 6.0)       # zoom in: the 0.2-radius object fills the frame
     rb = RayBundle.for_camera(torch.from_numpy(small.rays(None)).cuda(), small.origin, small.R_c2w, small.near, small.far)
     out = model.probe(rb)
     hit = out["ray_mask"].reshape(H, W).bool()
-    assert 0.2 < float(hit.float().mean()) < 1.0
+    assert 0.2 < float(hit.float().mean()) < 0.98, float(hit.float().mean())
     gt = torch.ones((H, W, 3), device="cuda")
     gt[~hit] = 0.3                       # the ground truth says there is an object where no neural point was found
     n0 = model.neural_points.points_xyz.shape[0]
