@@ -380,13 +380,14 @@ def bench_train(c, cam, steps, warmup):
     rb_dev = to_device(host, RayBundle)
     gt_host = torch.rand((TRAIN_RAYS, 3), generator=torch.Generator().manual_seed(9)).pin_memory()
     gt_dev = gt_host.cuda()
-    engine = TrainEngine(model, dist, exchange=c.exchange)     # the plugin's two Adam groups + exponential decay (studio_config.py:33-48)
+    # the plugin's two Adam groups + exponential decay (studio_config.py:33-48); the step is captured as one CUDA graph
+    engine = TrainEngine(model, dist, exchange=c.exchange, use_graph=not c.no_graph)
 
     def step_dev():
         engine.step(rb_dev, gt_dev)
 
     def step_e2e():
-        rb = to_device(host, RayBundle)
+        rb = RayBundle.for_camera(host[1].cuda(non_blocking=True), cam.origin, cam.R_c2w, cam.near, cam.far)
         loss = engine.step(rb, gt_host.cuda(non_blocking=True))
         loss.item()
 
@@ -412,7 +413,7 @@ def bench_train(c, cam, steps, warmup):
     for _ in range(5):
         if dist is not None:
             dist.barrier()
-        step_dev()
+        engine.update()          # on zero gradients: same traffic, same kernels
     torch.cuda.synchronize()
     ar_ms = statistics.median(a.elapsed_time(b) for a, b in engine.timing)
     engine.timing = None
@@ -423,11 +424,11 @@ def bench_train(c, cam, steps, warmup):
     ach = flops / (field_ms * 1e-3) / 1e12 if field_ms > 0 else 0.0
     n_pts = sum(p.numel() for p in model.get_param_groups()["neural_points"] if p.requires_grad)
     n_mlp = sum(p.numel() for p in model.get_param_groups()["fields"] if p.requires_grad)
-    h2d = sum(t.numel() * t.element_size() for t in host) + gt_host.numel() * 4
+    h2d = host[1].numel() * 4 + 14 * 4 + gt_host.numel() * 4
     rays_all = TRAIN_RAYS * world * steps
     return {"metric": "train rays/s", "value": rays_all / (ms_total * 1e-3), "unit": "rays/s", "ms_per_step": ms_total / steps,
             "steps": steps, "warmup": n_warm, "rays_per_step_per_gpu": TRAIN_RAYS,
-            "update_ms": ar_ms, "exchange": engine.exchange, "exchange_bytes": 4 * (n_pts + n_mlp) if dist is not None else 0,
+            "update_ms": ar_ms, "exchange": engine.exchange, "cuda_graph": bool(engine._graphs), "exchange_bytes": 4 * (n_pts + n_mlp) if dist is not None else 0,
             "update_is": "gradient exchange over the ranks + Adam on both groups + gradient reset (TrainEngine.update); at 1 GPU it is the "
                          "Adam pass alone, so the difference to the 1-GPU figure is the cost of the collective",
             "device_ms": {k: v for k, v in stage_ms.items()},
@@ -510,6 +511,7 @@ def main():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--with-scannet", action="store_true", help="add the configs[3] block at N = 1 too (always on at N > 1)")
     ap.add_argument("--no-scannet", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="train block: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="gradient exchange of the train block at N > 1")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -536,7 +538,7 @@ def main():
 
     c = Ctx()
     c.dist, c.world, c.rank, c.precision = dist, world, rank, precision
-    c.exchange = args.exchange
+    c.exchange, c.no_graph = args.exchange, args.no_graph
     c.peaks = load_peaks()
     c.weights = make_weights()
     c.flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device="cuda")     # 256 MB > 126 MB L2

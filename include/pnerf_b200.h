@@ -87,6 +87,9 @@ int pnerf_sample_select(const pnerf_grid_view* grid_h, const float* raypos, cons
 int pnerf_sample_select_jitter(const pnerf_grid_view* grid_h, const float* origin_h, const float* dirs, float near_t,
                                float far_t, float jitter, uint64_t seed, int R, int D, int SR, int fill_missed,
                                float* sample_loc, int* sample_cnt, void* stream);
+/* Same with origin / near / far / seed read from the device-side step constants (pnerf_camera.dev layout) at run time. */
+int pnerf_sample_select_jitter_dev(const pnerf_grid_view* grid_h, const float* step_dev, const float* dirs, float jitter, int R, int D,
+                                   int SR, int fill_missed, float* sample_loc, int* sample_cnt, void* stream);
 /* Hit-ray compaction (R -> R' of the reference's op, CU:381-391): ids of the rays with sample_cnt > 0, ascending, and their
  * rows of sample_loc / sample_cnt / dirs gathered into compact (R',.) arrays; every later stage then runs on R' rays. */
 int pnerf_hit_rays(const int* sample_cnt, int R, int* ray_index, int* n_rays, void* workspace, int64_t workspace_bytes,
@@ -138,7 +141,13 @@ typedef struct {
 typedef struct {
     float origin[3];      /* ray_bundle.origins[0]             (SU:152) */
     float R_c2w[9];       /* metadata["camrotc2w"], row major  (SU:148-151) */
+    /* Optional DEVICE copy of the per-step constants, PNERF_STEP_WORDS 32-bit words:
+     *   [0..2] origin, [3..11] R_c2w (row major), [12] near, [13] far, [14] jitter seed low word, [15] high word (as bits).
+     * When non-NULL the kernels read the camera (and pnerf_sample_select_jitter the near / far / seed) from it at RUN time and
+     * ignore the host values above: a CUDA graph captured once is replayed for every camera / step by rewriting these 64 bytes. */
+    const float* dev;
 } pnerf_camera;
+#define PNERF_STEP_WORDS 16
 
 typedef struct {          /* fp32 weights, torch nn.Linear layout (out,in) row major */
     const float *w1, *b1; /* mlp_base.layers.0  256x284  [aggregator.block1.0]       */
@@ -353,6 +362,9 @@ typedef struct {
     int64_t lo, hi, boundary, step;
     float lr[2];
     int world, rank;
+    /* optional DEVICE array of 3 floats {lr[0] / bias_correction1, lr[1] / bias_correction1, 1 / sqrt(bias_correction2)} read at
+     * run time instead of the values derived from lr / step above (CUDA-graph replay with a moving schedule) */
+    const float* hyper_dev;
 } pnerf_dp_adam;
 int pnerf_dp_adam_step(const pnerf_dp_adam* h, float beta1, float beta2, float eps, float grad_scale, void* stream);
 

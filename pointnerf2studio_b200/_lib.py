@@ -29,7 +29,7 @@ class Points(C.Structure):
 
 
 class Camera(C.Structure):
-    _fields_ = [("origin", C.c_float * 3), ("R_c2w", C.c_float * 9)]
+    _fields_ = [("origin", C.c_float * 3), ("R_c2w", C.c_float * 9), ("dev", C.c_void_p)]
 
 
 MLP_FIELDS = ["w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4", "wa", "ba",
@@ -56,7 +56,7 @@ class AdamSeg(C.Structure):
 
 class DpAdam(C.Structure):
     _fields_ = [("p", C.c_void_p * 8), ("g", C.c_void_p * 8), ("m", C.c_void_p), ("v", C.c_void_p), ("lo", C.c_int64), ("hi", C.c_int64),
-                ("boundary", C.c_int64), ("step", C.c_int64), ("lr", C.c_float * 2), ("world", C.c_int), ("rank", C.c_int)]
+                ("boundary", C.c_int64), ("step", C.c_int64), ("lr", C.c_float * 2), ("world", C.c_int), ("rank", C.c_int), ("hyper_dev", C.c_void_p)]
 
 
 class RenderBuffers(C.Structure):
@@ -85,6 +85,8 @@ SIGNATURES = {
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pnerf_sample_select_jitter": (C.c_int, [C.POINTER(GridView), C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,
                                              C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pnerf_sample_select_jitter_dev": (C.c_int, [C.POINTER(GridView), C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "pnerf_hit_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pnerf_gather_hit_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),

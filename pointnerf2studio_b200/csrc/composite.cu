@@ -10,7 +10,13 @@ namespace {
 
 constexpr int MAXC = 4;   // SR <= 128
 
-struct CompCam { float o[3]; float Rz[3]; };   // only the camera z axis matters for the depth
+struct CompCam { float o[3]; float Rz[3]; const float* dev; };   // only the camera z axis matters for the depth; dev: pnerf_camera.dev
+__device__ __forceinline__ void load_cam(CompCam& c) {
+    if (c.dev) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) { c.o[i] = __ldg(c.dev + i); c.Rz[i] = __ldg(c.dev + 3 + 3 * i + 2); }
+    }
+}
 
 // z of R_c2w^T (p - o), mul-then-add like SU:140-141
 __device__ __forceinline__ float depth_of(const CompCam& c, const float* __restrict__ p) {
@@ -78,6 +84,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(CompCam cam, pnerf_m
                                                              const float* __restrict__ sigma, const float* __restrict__ rgb,
                                                              int R, int SR, float* __restrict__ out_rgb,
                                                              float* __restrict__ out_w, float* __restrict__ out_T) {
+    load_cam(cam);
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
@@ -122,6 +129,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(CompCam cam, pnerf_m
                                                              const float* __restrict__ sigma, const float* __restrict__ rgb,
                                                              const float* __restrict__ d_out, int R, int SR,
                                                              float* __restrict__ d_sigma, float* __restrict__ d_rgb) {
+    load_cam(cam);
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
@@ -295,6 +303,7 @@ __global__ void __launch_bounds__(256) probe_kernel(CompCam cam, pnerf_mode mode
 CompCam make_ccam(const pnerf_camera* c) {
     CompCam k;
     for (int i = 0; i < 3; i++) { k.o[i] = c->origin[i]; k.Rz[i] = c->R_c2w[3 * i + 2]; }
+    k.dev = c->dev;
     return k;
 }
 int ray_blocks(int R) {

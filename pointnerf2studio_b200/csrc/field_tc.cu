@@ -82,6 +82,7 @@ constexpr int WPACK_FIELD_BYTES = (36 + 34 + 36 + 34) * HID * 16;          // 57
 constexpr int WPACK_BYTES = WPACK_FIELD_BYTES + C1_BYTES + 2 * C2_BYTES;   // 696320
 
 struct Cam { float o[3]; float Rc[9]; float Rw[9]; };
+struct CamOR { float o[3]; float Rc[9]; };    // the per-step part (pnerf_camera.dev words 0..11)
 
 struct Meta {                       // per (slot, tile parity): written by the encoder, read by the slot's aggregation epilogue
     float w[ROWS];                  // aggregation weight of the row (0 for masked rows)
@@ -100,6 +101,7 @@ struct Smem {
     uint64_t w_full[NGRP], w_empty[NGRP], w_peer[NGRP];
     uint64_t a_ready[2], acc_full[2], acc_empty[2], a_free[2];
     uint32_t tmem_base;
+    CamOR cam;                          // camera origin / rotation: the launch parameters, or the device-side step constants (graph replay)
 };
 
 static_assert(sizeof(Smem) <= 232448, "field_tc_kernel shared memory exceeds the 227 KB per-CTA limit");
@@ -111,6 +113,7 @@ struct FieldParams {
     const uint8_t* wpack;
     const float *wa, *ba;                    // density head (the four layer biases ride in the packed weights)
     Cam cam;
+    const float* cam_dev;           // pnerf_camera.dev: per-step camera read at run time, or NULL
     int S, SR, K, n_tiles;          // S / n_tiles: host-side CAPACITY when S_dev is set (grid and workspace are sized from it)
     const int* S_dev;               // device-side number of valid samples (<= S), or NULL: the host does not know S and never syncs for it
     float slope;
@@ -140,7 +143,8 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
     return r;
 }
 
-__device__ __forceinline__ void to_pers(const Cam& c, float x, float y, float z, float& px, float& py, float& pz) {
+template <class C_>
+__device__ __forceinline__ void to_pers(const C_& c, float x, float y, float z, float& px, float& py, float& pz) {
     const float sx = x - c.o[0], sy = y - c.o[1], sz = z - c.o[2];
     const float cx = sx * c.Rc[0] + sy * c.Rc[3] + sz * c.Rc[6];
     const float cy = sx * c.Rc[1] + sy * c.Rc[4] + sz * c.Rc[7];
@@ -210,7 +214,7 @@ struct RowSink {
 // Both recompute the (cheap) geometry.  The encoder sits on the critical path at every tile boundary -- a slot's A buffer is only
 // free once its layer-4 MMAs are done -- so its latency, not its throughput, is what the split buys.
 template <int KP, bool SAVE, int PART>
-__device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int pidx, uint8_t* Abuf, uint8_t* gsave, Meta& meta,
+__device__ __forceinline__ void encode_tile(const FieldParams& p, const CamOR& camor, int slot, int pidx, uint8_t* Abuf, uint8_t* gsave, Meta& meta,
                                             SlotScratch& scr, int row) {
     const int k = row % KP;
     if (PART == 1 && k == 0) meta.slot_id[row / KP] = slot;
@@ -244,8 +248,13 @@ __device__ __forceinline__ void encode_tile(const FieldParams& p, int slot, int 
         if (PART == 0) {
             // geometry (SM:273-281) and PE(dists6, F=5) 60 | 0 x 4
             float spx, spy, spz, ppx, ppy, ppz;
-            to_pers(p.cam, sx, sy, sz, spx, spy, spz);
-            to_pers(p.cam, X, Y, Z, ppx, ppy, ppz);
+            if (p.cam_dev) {      // graph replay: this step's camera from shared memory (warp-uniform branch)
+                to_pers(camor, sx, sy, sz, spx, spy, spz);
+                to_pers(camor, X, Y, Z, ppx, ppy, ppz);
+            } else {              // launch parameters: constant-bank operands, no loads
+                to_pers(p.cam, sx, sy, sz, spx, spy, spz);
+                to_pers(p.cam, X, Y, Z, ppx, ppy, ppz);
+            }
             d[3] = ppx * ppz - spx * spz; d[4] = ppy * ppz - spy * spz; d[5] = ppz - spz;
             float d3[3];
             rot_w2c(p.cam, d, d3);                                                              // SM:312
@@ -545,6 +554,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
         fence_barrier_init();
     }
     if (warp == ENCW + 2 * EPW + 1) tmem_alloc2(&sm.tmem_base, 512);
+    if (tid < 12) {
+        float* dst = tid < 3 ? &sm.cam.o[tid] : &sm.cam.Rc[tid - 3];
+        *dst = p.cam_dev ? __ldg(p.cam_dev + tid) : (tid < 3 ? p.cam.o[tid] : p.cam.Rc[tid - 3]);
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();          // both CTAs' barriers exist before any remote arrive / multicast commit
@@ -568,8 +581,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
             if (j >= 2) { mbar_wait(&sm.a_free[s], ph[s]); ph[s] ^= 1; }
             tr.ev(1);
             uint8_t* gsave = SAVE ? p.save + (int64_t)tile_of(j) * SAVE_TILE_BYTES : nullptr;
-            if (ENC_PARTS == 1 || part == 0) encode_tile<KP, SAVE, 0>(p, slot0, pidx0, sm.A[s], gsave, sm.meta[s][(j >> 1) & 1], sm.scratch[s], erow);
-            if (ENC_PARTS == 1 || part == 1) encode_tile<KP, SAVE, 1>(p, slot0, pidx0, sm.A[s], gsave, sm.meta[s][(j >> 1) & 1], sm.scratch[s], erow);
+            if (ENC_PARTS == 1 || part == 0) encode_tile<KP, SAVE, 0>(p, sm.cam, slot0, pidx0, sm.A[s], gsave, sm.meta[s][(j >> 1) & 1], sm.scratch[s], erow);
+            if (ENC_PARTS == 1 || part == 1) encode_tile<KP, SAVE, 1>(p, sm.cam, slot0, pidx0, sm.A[s], gsave, sm.meta[s][(j >> 1) & 1], sm.scratch[s], erow);
             slot0 = slot1; pidx0 = pidx1; slot1 = slot2; pidx1 = pidx2;
             fence_proxy_async();
             __syncwarp();
@@ -1024,6 +1037,7 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     p.wpack = (const uint8_t*)wpack;
     p.wa = mlp->wa; p.ba = mlp->ba;
     p.cam = make_cam(pts, cam);
+    p.cam_dev = cam->dev;
     p.S = S; p.S_dev = S_dev; p.SR = SR; p.K = K;
     const int spt = ROWS / KP;
     p.n_tiles = (S + spt - 1) / spt;

@@ -59,6 +59,7 @@ struct DpArgs {
     float *m, *v;
     int64_t lo, hi, boundary;
     float lr_c[2], inv_bc2_sqrt;
+    const float* hyper_dev;          // {lr_c[0], lr_c[1], inv_bc2_sqrt} in device memory (graph replay), or NULL
     int world, me;
 };
 
@@ -66,6 +67,8 @@ template <int W>
 __global__ void __launch_bounds__(512) dp_adam_kernel(const DpArgs a, float omb1, float b2, float omb2, float eps, float gscale) {
     const int64_t n4 = (a.hi - a.lo) >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float lrc0 = a.hyper_dev ? __ldg(a.hyper_dev) : a.lr_c[0], lrc1 = a.hyper_dev ? __ldg(a.hyper_dev + 1) : a.lr_c[1];
+    const float ibc2 = a.hyper_dev ? __ldg(a.hyper_dev + 2) : a.inv_bc2_sqrt;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const int64_t e = a.lo + 4 * i;
         float4 gs[W];
@@ -77,12 +80,12 @@ __global__ void __launch_bounds__(512) dp_adam_kernel(const DpArgs a, float omb1
         g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale;
         float4 p = *reinterpret_cast<const float4*>(a.p[a.me] + e);
         float4 m = reinterpret_cast<float4*>(a.m)[i], v = reinterpret_cast<float4*>(a.v)[i];
-        const float l0 = e + 0 < a.boundary ? a.lr_c[0] : a.lr_c[1], l1 = e + 1 < a.boundary ? a.lr_c[0] : a.lr_c[1];
-        const float l2 = e + 2 < a.boundary ? a.lr_c[0] : a.lr_c[1], l3 = e + 3 < a.boundary ? a.lr_c[0] : a.lr_c[1];
-        adam1(p.x, g.x, m.x, v.x, l0, omb1, b2, omb2, eps, a.inv_bc2_sqrt);
-        adam1(p.y, g.y, m.y, v.y, l1, omb1, b2, omb2, eps, a.inv_bc2_sqrt);
-        adam1(p.z, g.z, m.z, v.z, l2, omb1, b2, omb2, eps, a.inv_bc2_sqrt);
-        adam1(p.w, g.w, m.w, v.w, l3, omb1, b2, omb2, eps, a.inv_bc2_sqrt);
+        const float l0 = e + 0 < a.boundary ? lrc0 : lrc1, l1 = e + 1 < a.boundary ? lrc0 : lrc1;
+        const float l2 = e + 2 < a.boundary ? lrc0 : lrc1, l3 = e + 3 < a.boundary ? lrc0 : lrc1;
+        adam1(p.x, g.x, m.x, v.x, l0, omb1, b2, omb2, eps, ibc2);
+        adam1(p.y, g.y, m.y, v.y, l1, omb1, b2, omb2, eps, ibc2);
+        adam1(p.z, g.z, m.z, v.z, l2, omb1, b2, omb2, eps, ibc2);
+        adam1(p.w, g.w, m.w, v.w, l3, omb1, b2, omb2, eps, ibc2);
         reinterpret_cast<float4*>(a.m)[i] = m;
         reinterpret_cast<float4*>(a.v)[i] = v;
 #pragma unroll
@@ -106,6 +109,7 @@ extern "C" int pnerf_dp_adam_step(const pnerf_dp_adam* h, float beta1, float bet
         a.p[i] = h->p[w]; a.g[i] = h->g[w];
     }
     a.me = 0;
+    a.hyper_dev = h->hyper_dev;
     a.m = h->m; a.v = h->v; a.lo = h->lo; a.hi = h->hi; a.boundary = h->boundary; a.world = h->world;
     const double bc1 = 1.0 - pow((double)beta1, (double)h->step), bc2 = 1.0 - pow((double)beta2, (double)h->step);
     a.lr_c[0] = (float)(h->lr[0] / bc1); a.lr_c[1] = (float)(h->lr[1] / bc1); a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));

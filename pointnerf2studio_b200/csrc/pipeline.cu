@@ -35,6 +35,8 @@ extern "C" int pnerf_render_train_forward(const pnerf_grid_view* grid, const pne
     if (phases & 1) {
         if (t_vals)
             rc = pnerf_sample_select(grid, nullptr, cam->origin, dirs, t_vals, t_stride, R, D, SR, 1, b->sample_loc, b->sample_cnt, stream);
+        else if (cam->dev)      // camera / near / far / seed from the device-side step constants (CUDA-graph replay)
+            rc = pnerf_sample_select_jitter_dev(grid, cam->dev, dirs, jitter, R, D, SR, 1, b->sample_loc, b->sample_cnt, stream);
         else
             rc = pnerf_sample_select_jitter(grid, cam->origin, dirs, near_t, far_t, jitter, seed, R, D, SR, 1, b->sample_loc, b->sample_cnt, stream);
         if (rc) return rc;

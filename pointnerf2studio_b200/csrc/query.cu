@@ -110,8 +110,14 @@ __global__ void __launch_bounds__(256, MODE == 2 ? PNERF_SEL_MINB : 1) sample_se
                                                              const float* __restrict__ raypos, float ox, float oy, float oz,
                                                              const float* __restrict__ dirs, const float* __restrict__ t_vals,
                                                              int t_stride, TGen gen, int R, int D, int SR, int fill_missed,
-                                                             float* __restrict__ sample_loc, int* __restrict__ sample_cnt) {
+                                                             float* __restrict__ sample_loc, int* __restrict__ sample_cnt,
+                                                             const float* __restrict__ step_dev) {
     const int lane = threadIdx.x & 31;
+    if (step_dev) {          // per-step constants from device memory (CUDA-graph replay): pnerf_camera.dev layout
+        ox = __ldg(step_dev); oy = __ldg(step_dev + 1); oz = __ldg(step_dev + 2);
+        gen.near = __ldg(step_dev + 12); gen.far = __ldg(step_dev + 13);
+        gen.seed_lo = __float_as_uint(__ldg(step_dev + 14)); gen.seed_hi = __float_as_uint(__ldg(step_dev + 15));
+    }
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
         float d[3] = {0.f, 0.f, 0.f};
@@ -367,10 +373,10 @@ extern "C" int pnerf_sample_select(const pnerf_grid_view* g, const float* raypos
     cudaStream_t st = (cudaStream_t)stream;
     if (raypos)
         sample_select_kernel<0><<<ray_warps_grid(R), 256, 0, st>>>(f, g->occ_bits, raypos, 0.f, 0.f, 0.f, nullptr, nullptr, 0, gen, R, D, SR,
-                                                                  fill_missed, sample_loc, sample_cnt);
+                                                                  fill_missed, sample_loc, sample_cnt, nullptr);
     else
         sample_select_kernel<1><<<ray_warps_grid(R), 256, 0, st>>>(f, g->occ_bits, nullptr, origin_h[0], origin_h[1], origin_h[2], dirs,
-                                                                  t_vals, t_stride, gen, R, D, SR, fill_missed, sample_loc, sample_cnt);
+                                                                  t_vals, t_stride, gen, R, D, SR, fill_missed, sample_loc, sample_cnt, nullptr);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }
@@ -385,7 +391,20 @@ extern "C" int pnerf_sample_select_jitter(const pnerf_grid_view* g, const float*
     const TGen gen = {near, far, jitter, (uint32_t)seed, (uint32_t)(seed >> 32)};
     sample_select_kernel<2><<<ray_warps_grid(R), 256, 0, (cudaStream_t)stream>>>(f, g->occ_bits, nullptr, origin_h[0], origin_h[1],
                                                                                 origin_h[2], dirs, nullptr, 0, gen, R, D, SR,
-                                                                                fill_missed, sample_loc, sample_cnt);
+                                                                                fill_missed, sample_loc, sample_cnt, nullptr);
+    PNERF_LAUNCH_CHECK();
+    return PNERF_OK;
+}
+
+extern "C" int pnerf_sample_select_jitter_dev(const pnerf_grid_view* g, const float* step_dev, const float* dirs, float jitter, int R, int D,
+                                              int SR, int fill_missed, float* sample_loc, int* sample_cnt, void* stream) {
+    if (!g || R < 0 || D <= 0 || SR <= 0 || !step_dev) return PNERF_ERR_ARG;
+    if (R == 0) return PNERF_OK;
+    if (!sample_loc || !sample_cnt || !g->occ_bits || !dirs) return PNERF_ERR_ARG;
+    const Frame f = frame_of(g);
+    const TGen gen = {0.f, 1.f, jitter, 0u, 0u};
+    sample_select_kernel<2><<<ray_warps_grid(R), 256, 0, (cudaStream_t)stream>>>(f, g->occ_bits, nullptr, 0.f, 0.f, 0.f, dirs, nullptr, 0, gen, R, D,
+                                                                                SR, fill_missed, sample_loc, sample_cnt, step_dev);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }

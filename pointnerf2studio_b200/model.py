@@ -505,6 +505,12 @@ class PointNerf(_ModelBase):
         finally:
             native.unpin_stream()
 
+    def set_step_consts(self, step_consts=None):
+        """A device tensor of 16 fp32 words (pnerf_camera.dev layout) the training kernels read the camera / near / far / jitter
+        seed from at run time, instead of the by-value launch parameters: what makes a captured CUDA graph of the training step
+        replayable for every batch (parallel.TrainEngine writes it before each replay).  None switches it off."""
+        self._step_consts = step_consts
+
     def set_grad_sink(self, sink_points=None, sink_mlp=None, points_done_event=0):
         """A data-parallel trainer (parallel.TrainEngine) hands the backward kernels the flat buffers the gradients are to be
         accumulated in (`.grad` of the parameters aliases them) and, optionally, a CUDA event to record as soon as the point
@@ -530,14 +536,17 @@ class PointNerf(_ModelBase):
             t_stride = 0 if t_vals.dim() == 1 else c.z_depth_dim
         mode = native.make_mode(c.flow, training=self.training, bg=self._background_color.tolist(), vsize_z=c.vsize[2])
         params = self.mlp_param_list()
-        wpack = native_tc.packed_weights(params)[0]
+        wpack = native_tc.packed_weights(params, force=self.__dict__.get("_force_repack", False))[0]
         sink_points, sink_mlp, event = self.__dict__.get("_grad_sink", (None, None, 0))
+        step_consts = self.__dict__.get("_step_consts")
+        if step_consts is not None and t_vals is not None:
+            raise RuntimeError("step constants on the device need the in-kernel jitter (jitter > 0, no generator)")
         fl, it = ops.fl_it(grid.frame, origin, R_c2w, native._rw2c_host(npnts.points_Rw2c), near, far, jitter, float(npnts.radius_limit_np),
                            mode, c.z_depth_dim, c.SR, c.K, int(npnts.kernel_size[0]), seed=seed, t_stride=t_stride, event=event)
         (rgb, ray_mask, n_rays, pidx, loc, valid, cnt, sigma, srgb, ids, n_samples, _ws, _ridx) = torch.ops.pnerf.render_train(
             dirs, npnts.points_xyz, npnts.points_embeding.view(-1, c.point_features_dim), npnts.points_color.view(-1, 3),
             npnts.points_dir.view(-1, 3), npnts.points_conf.view(-1, 1), [p for p in params], wpack, grid.cell_start, grid.recs,
-            grid.occ_bits, t_vals, sink_points, sink_mlp, fl, it)
+            grid.occ_bits, t_vals, sink_points, sink_mlp, step_consts, fl, it)
         out = {"coarse_raycolor": rgb, "ray_mask": ray_mask,
                "conf_coefficient": ConfCoefficient(npnts.points_conf, pidx, ray_mask, n_rays)}
         self._last_query = native.QueryResult(loc, cnt, pidx, valid)

@@ -17,13 +17,19 @@ _PACK_CACHE = {}
 MAX_SAMPLES_PER_LAUNCH = 1 << 23      # valid samples per field-kernel launch (4.3 GB of bf16 features); a memory knob only
 
 
-def packed_weights(mlp_params):
-    """bf16 K-slab copy of the seven weight matrices, re-packed only when a parameter changed."""
+def packed_weights(mlp_params, force: bool = False):
+    """bf16 K-slab copy of the seven weight matrices, re-packed only when a parameter changed (force: always, into the SAME
+    buffer -- the pack launch of a training step has to be part of a captured CUDA graph)."""
     lib = _lib.load()
     key = tuple((p.data_ptr(), p._version) for p in mlp_params)
     dev = mlp_params[0].device
     hit = _PACK_CACHE.get(dev)
-    if hit is not None and hit[0] == key:
+    if hit is not None and hit[0] == key and not force:
+        return hit[1], hit[2], hit[3]
+    if hit is not None and force and tuple(k[0] for k in hit[0]) == tuple(k[0] for k in key):      # same storages: re-pack in place
+        check(lib.pnerf_tc_pack_weights(C.byref(hit[2]), _ptr(hit[1]), _stream()), "pnerf_tc_pack_weights")
+        LAUNCHES["n"] += 1
+        _PACK_CACHE[dev] = (key, hit[1], hit[2], hit[3])
         return hit[1], hit[2], hit[3]
     names = [n for _, w, b in MLP_PARAM_NAMES for n in (w, b)]
     params = dict(zip(names, [p.detach().contiguous() for p in mlp_params]))

@@ -48,7 +48,7 @@ def _p(t: Optional[Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _structs(fl, it, xyz, embed, color, dirn, conf, mlp, grid=None):
+def _structs(fl, it, xyz, embed, color, dirn, conf, mlp, grid=None, step_consts=None):
     pts = Points()
     pts.xyz, pts.embed, pts.color, pts.dir, pts.conf = xyz.data_ptr(), embed.data_ptr(), color.data_ptr(), dirn.data_ptr(), conf.data_ptr()
     pts.Rw2c = (C.c_float * 9)(*fl[FL_RW2C:FL_RW2C + 9])
@@ -56,6 +56,9 @@ def _structs(fl, it, xyz, embed, color, dirn, conf, mlp, grid=None):
     cam = Camera()
     cam.origin = (C.c_float * 3)(*fl[FL_ORIGIN:FL_ORIGIN + 3])
     cam.R_c2w = (C.c_float * 9)(*fl[FL_RC2W:FL_RC2W + 9])
+    if step_consts is not None:       # camera / near / far / seed read from device memory at run time (CUDA-graph replay)
+        assert step_consts.is_cuda and step_consts.dtype == torch.float32 and step_consts.numel() >= 16 and step_consts.is_contiguous()
+        cam.dev = step_consts.data_ptr()
     m = Mlp()
     for name, t in zip(_lib.MLP_FIELDS, mlp):
         setattr(m, name, t.data_ptr())
@@ -88,13 +91,16 @@ RenderOut = Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor
 @torch.library.custom_op("pnerf::render_train", mutates_args=())
 def render_train(dirs: Tensor, xyz: Tensor, embed: Tensor, color: Tensor, dirn: Tensor, conf: Tensor, mlp: List[Tensor],
                  wpack: Tensor, cell_start: Tensor, recs: Tensor, occ_bits: Tensor, t_vals: Optional[Tensor],
-                 sink_points: Optional[Tensor], sink_mlp: Optional[Tensor], fl: List[float], it: List[int]) -> RenderOut:
+                 sink_points: Optional[Tensor], sink_mlp: Optional[Tensor], step_consts: Optional[Tensor], fl: List[float],
+                 it: List[int]) -> RenderOut:
     """-> (out_rgb (R,3), ray_mask (R) i8, n_rays (1) i32, sample_pidx (R,SR,K) i32, sample_loc (R,SR,3), sample_valid (R,SR) u8,
            sample_cnt (R) i32, sigma (R,SR), rgb (R,SR,3), sample_ids (R*SR) i32, n_samples (1) i32, workspace u8, ray_index (R) i32)
 
     sink_points / sink_mlp (optional): flat fp32 buffers [embed N*32 | color N*3 | dir N*3 | conf N] / the 18 MLP tensors back to
     back.  When given, the backward pass accumulates (+=) straight into them and returns no gradient for those inputs -- a
-    data-parallel trainer aliases `.grad` to them so the collective runs in place (parallel.DataParallelTrainer)."""
+    data-parallel trainer aliases `.grad` to them so the collective runs in place (parallel.TrainEngine).
+    step_consts (optional): 16 fp32 words on the device (pnerf_camera.dev layout: origin, R_c2w, near, far, jitter seed bits); the
+    kernels then read the camera / near / far / seed from it at run time, so a captured CUDA graph serves every step."""
     lib = _lib.load()
     _check_inputs(dirs, xyz, embed, color, dirn, conf, mlp)
     R, dev = dirs.shape[0], dirs.device
@@ -117,7 +123,7 @@ def render_train(dirs: Tensor, xyz: Tensor, embed: Tensor, color: Tensor, dirn: 
         n_rays.zero_(); n_samples.zero_()
         return (out_rgb, ray_mask, n_rays, sample_pidx, sample_loc, sample_valid, sample_cnt, sigma, rgb, sample_ids, n_samples,
                 torch.empty((256,), dtype=torch.uint8, device=dev), ray_index)
-    pts, cam, m, mode, gv = _structs(fl, it, xyz, embed, color, dirn, conf, mlp, (cell_start, recs, occ_bits))
+    pts, cam, m, mode, gv = _structs(fl, it, xyz, embed, color, dirn, conf, mlp, (cell_start, recs, occ_bits), step_consts)
     scratch_bytes = lib.pnerf_render_train_scratch_bytes(R, SR)
     scratch = torch.empty((scratch_bytes,), dtype=torch.uint8, device=dev)
     b = RenderBuffers()
@@ -153,7 +159,7 @@ def render_train(dirs: Tensor, xyz: Tensor, embed: Tensor, color: Tensor, dirn: 
 
 
 @render_train.register_fake
-def _(dirs, xyz, embed, color, dirn, conf, mlp, wpack, cell_start, recs, occ_bits, t_vals, sink_points, sink_mlp, fl, it):
+def _(dirs, xyz, embed, color, dirn, conf, mlp, wpack, cell_start, recs, occ_bits, t_vals, sink_points, sink_mlp, step_consts, fl, it):
     R, SR, K = dirs.shape[0], it[IT_SR], it[IT_K]
     e = lambda shape, dt: dirs.new_empty(shape, dtype=dt)
     ws = torch.library.get_ctx().new_dynamic_size()
@@ -163,11 +169,12 @@ def _(dirs, xyz, embed, color, dirn, conf, mlp, wpack, cell_start, recs, occ_bit
 
 
 def _render_train_setup(ctx, inputs, output):
-    (dirs, xyz, embed, color, dirn, conf, mlp, wpack, cell_start, recs, occ_bits, t_vals, sink_points, sink_mlp, fl, it) = inputs
+    (dirs, xyz, embed, color, dirn, conf, mlp, wpack, cell_start, recs, occ_bits, t_vals, sink_points, sink_mlp, step_consts, fl, it) = inputs
     (out_rgb, ray_mask, n_rays, sample_pidx, sample_loc, sample_valid, sample_cnt, sigma, rgb, sample_ids, n_samples, ws, ray_index) = output
     ctx.save_for_backward(dirs, xyz, embed, color, dirn, conf, *mlp, sample_pidx, sample_loc, sample_valid, sample_ids, n_samples, sigma, rgb, ws)
     ctx.fl, ctx.it = list(fl), list(it)
     ctx.sinks = (sink_points, sink_mlp)
+    ctx.step_consts = step_consts
     # autograd must NOT materialise zero gradients for the outputs nobody differentiates: one of them is the multi-GB workspace
     # (a zeros_like of it costs 4 ms per step), the others are index tensors
     ctx.set_materialize_grads(False)
@@ -183,14 +190,14 @@ def _render_train_backward(ctx, d_out, *unused):
     fl, it = ctx.fl, ctx.it
     sink_points, sink_mlp = ctx.sinks
     R, SR, K = dirs.shape[0], it[IT_SR], it[IT_K]
-    n_in = 16
+    n_in = 17
     if d_out is None or R == 0:
         return (None,) * 6 + ([None] * len(MLP_NUMEL),) + (None,) * (n_in - 7)
     dev = dirs.device
     N = xyz.shape[0]
     need = ctx.needs_input_grad      # per input; a list of flags for the List[Tensor] input
     d_out = d_out.contiguous().float()
-    pts, cam, m, mode, _ = _structs(fl, it, xyz, embed, color, dirn, conf, mlp)
+    pts, cam, m, mode, _ = _structs(fl, it, xyz, embed, color, dirn, conf, mlp, None, ctx.step_consts)
     if sink_points is not None:
         assert sink_points.numel() == N * 39 and sink_points.is_contiguous() and sink_points.dtype == torch.float32
         g_embed, g_color, g_dir, g_conf = (sink_points[:N * 32], sink_points[N * 32:N * 35], sink_points[N * 35:N * 38], sink_points[N * 38:])
@@ -231,7 +238,7 @@ def _render_train_backward(ctx, d_out, *unused):
               "pnerf_render_train_backward")
     native.LAUNCHES["n"] += 18
     mlp_ret = [None] * len(MLP_NUMEL) if sink_mlp is not None else views
-    return (None, None, *ret_pts, mlp_ret, None, None, None, None, None, None, None, None, None)
+    return (None, None, *ret_pts, mlp_ret, None, None, None, None, None, None, None, None, None, None)
 
 
 render_train.register_autograd(_render_train_backward, setup_context=_render_train_setup)

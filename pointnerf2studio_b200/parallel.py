@@ -10,9 +10,15 @@ zeros (DDP's find_unused_parameters behaviour).
 from __future__ import annotations
 
 import os
+import types
 from typing import Iterable, List
 
 import torch
+
+
+def _as_i32(u: int) -> int:
+    u &= 0xffffffff
+    return u - (1 << 32) if u >= (1 << 31) else u
 
 
 def shard_rays(n_rays: int, rank: int, world: int):
@@ -177,7 +183,8 @@ class TrainEngine:
     """
 
     def __init__(self, model, dist=None, exchange: str = "auto", lr_fields: float = 5e-4, lr_points: float = 2e-3,
-                 lr_decay_exp: float = 0.1, lr_decay_iters: int = 1000000, betas=(0.9, 0.999), eps: float = 1e-8):
+                 lr_decay_exp: float = 0.1, lr_decay_iters: int = 1000000, betas=(0.9, 0.999), eps: float = 1e-8,
+                 use_graph: bool = False):
         from . import _lib
         self.model, self.dist = model, dist
         self.world = dist.get_world_size() if dist is not None else 1
@@ -186,6 +193,8 @@ class TrainEngine:
         self.decay = (float(lr_decay_exp), float(lr_decay_iters))
         self.betas, self.eps, self.steps = betas, float(eps), 0
         self.timing = None           # set to a list to collect (start, end) CUDA-event pairs around update()
+        self.use_graph = bool(use_graph)
+        self._graphs = {}            # number of rays -> captured step
         self._lib = _lib.load()
         npnts = model.neural_points
         dev = npnts.points_xyz.device
@@ -253,8 +262,9 @@ class TrainEngine:
         loss.backward()
         self.update()
 
-    def update(self):
-        """Gradient exchange + Adam + gradient reset, all enqueued on the current stream (nothing blocks the host)."""
+    def update(self, hyper_dev=None):
+        """Gradient exchange + Adam + gradient reset, all enqueued on the current stream (nothing blocks the host).
+        hyper_dev: device tensor {lr_points / bc1, lr_fields / bc1, 1 / sqrt(bc2)} read by the kernel at run time (graph replay)."""
         import ctypes as C
         from . import _lib
         lr_p, lr_f = self.lrs()
@@ -283,6 +293,8 @@ class TrainEngine:
             a.world, a.rank = 1, 0
         a.m, a.v = self.m.data_ptr(), self.v.data_ptr()
         a.lo, a.hi, a.boundary, a.step = self.lo, self.hi, self.boundary, self.steps
+        if hyper_dev is not None:
+            a.hyper_dev = hyper_dev.data_ptr()
         a.lr = (C.c_float * 2)(lr_p, lr_f)
         _lib.check(self._lib.pnerf_dp_adam_step(C.byref(a), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
                                                 C.c_float(1.0 / W), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pnerf_dp_adam_step")
@@ -296,8 +308,96 @@ class TrainEngine:
             t1.record()
             self.timing.append((t0, t1))
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    def _hyper(self, step):
+        """What pnerf_dp_adam_step derives on the host for 1-based optimiser step `step` (bias corrections in double, as torch)."""
+        f = pow(self.decay[0], (step - 1) / self.decay[1])
+        bc1, bc2 = 1.0 - self.betas[0] ** step, 1.0 - self.betas[1] ** step
+        return [self.lr0[0] * f / bc1, self.lr0[1] * f / bc1, 1.0 / (bc2 ** 0.5)]
+
+    def _consts(self, ray_bundle, step):
+        """The 19 words a replay needs: camera, near / far, jitter seed (pnerf_camera.dev layout) + the Adam step scalars."""
+        npnts = self.model.neural_points
+        origin, R_c2w, near, far = npnts.camera_of(ray_bundle, with_near_far=True)
+        npnts._jitter_calls += 1
+        seed = (int(self.model.config.jitter_seed) << 32) | (npnts._jitter_calls & 0xffffffff)
+        npnts._last_jitter = (near, far, float(self.model.config.jitter), seed)
+        vals = [float(v) for v in origin] + [float(v) for v in R_c2w.reshape(-1)] + [float(near), float(far)]
+        host = torch.tensor(vals + [0.0, 0.0] + self._hyper(step), dtype=torch.float32)
+        iv = host.view(torch.int32)
+        iv[14], iv[15] = _as_i32(seed & 0xffffffff), _as_i32(seed >> 32)
+        return host
+
+    def _capture(self, ray_bundle, image):
+        from .model import RayBundle
+        dev = self.P.device
+        R = ray_bundle.directions.shape[0]
+        c = types.SimpleNamespace()
+        c.dirs = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        c.gt = torch.empty((R, 3), dtype=torch.float32, device=dev)
+        c.consts = torch.zeros((19,), dtype=torch.float32, device=dev)
+        origin, R_c2w, near, far = self.model.neural_points.camera_of(ray_bundle, with_near_far=True)
+        cam = torch.zeros((14,), dtype=torch.float32, device=dev)
+        c.bundle = RayBundle(origins=cam[0:3].view(1, 3).expand(R, 3), directions=c.dirs, nears=cam[12:13].view(1, 1).expand(R, 1),
+                             fars=cam[13:14].view(1, 1).expand(R, 1),
+                             metadata={"camrotc2w": cam[3:12].view(3, 3),
+                                       "camera_host": {"origin": origin, "camrotc2w": R_c2w, "near": near, "far": far}})
+        c.dirs.copy_(ray_bundle.directions)
+        c.gt.copy_(image)
+        self.model.set_step_consts(c.consts[:16])
+        self.model._force_repack = True          # the bf16 weight pack is a launch of every step: it has to be inside the graph
+        hyper = c.consts[16:19]
+
+        def eager():
+            out = self.model.get_outputs(c.bundle)
+            loss = sum(self.model.get_loss_dict(out, {"image": c.gt}).values())
+            loss.backward()
+            self.update(hyper)
+            return loss
+
+        calls0, steps0 = self.model.neural_points._jitter_calls, self.steps
+        # warm-up on a side stream (allocator pools, lazy module state), with learning rates of zero so that nothing moves
+        c.consts.copy_(self._consts(ray_bundle, 1))
+        c.consts[16:18] = 0.0
+        keep_m, keep_v = self.m.clone(), self.v.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                eager()
+        torch.cuda.current_stream().wait_stream(side)
+        c.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(c.graph):
+            c.loss = eager()
+        # warm-up and capture ran Adam's moment updates with real gradients: restore the state (the parameters did not move: lr 0)
+        self.m.copy_(keep_m); self.v.copy_(keep_v)
+        self.steps = steps0
+        self.model.neural_points._jitter_calls = calls0
+        self.model.set_step_consts(None)
+        self.model._force_repack = False
+        torch.cuda.synchronize()
+        return c
+
+    def step_graph(self, ray_bundle, image):
+        R = ray_bundle.directions.shape[0]
+        c = self._graphs.get(R)
+        if c is None:
+            c = self._graphs[R] = self._capture(ray_bundle, image)
+        self.steps += 1
+        c.consts.copy_(self._consts(ray_bundle, self.steps))      # pageable -> device: staged synchronously, safe to rebuild next step
+        c.dirs.copy_(ray_bundle.directions, non_blocking=True)
+        c.gt.copy_(image, non_blocking=True)
+        c.graph.replay()
+        torch.autograd.graph.increment_version(self.params)
+        return c.loss
+
     def step(self, ray_bundle, image):
-        """-> the (rank-local) loss tensor; nothing is read back."""
+        """-> the (rank-local) loss tensor; nothing is read back.  With use_graph the whole step (forward, losses, backward,
+        exchange, Adam) is ONE captured CUDA graph per batch size, replayed after three small copies (directions, ground truth,
+        19 step constants): the host cost of a step drops from ~1.7 ms of Python to ~0.1 ms."""
+        if (self.use_graph and self.exchange in ("local", "p2p") and float(self.model.config.jitter) > 0 and self.model.training
+                and self.model.config.precision == "bf16"):
+            return self.step_graph(ray_bundle, image)
         out = self.model.get_outputs(ray_bundle)
         loss_dict = self.model.get_loss_dict(out, {"image": image})
         loss = sum(loss_dict.values())

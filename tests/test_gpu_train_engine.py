@@ -124,3 +124,42 @@ def test_conf_coefficient_behaves_as_the_reference_tensor():
     loss_ref = 1e-4 * torch.mean(torch.log(ref) + torch.log(1 - ref))
     ld = model.get_loss_dict(out, {"image": torch.zeros((len(pix), 3)).cuda()})
     assert abs(float(loss_ref) - float(ld["conf_coefficient_loss"])) <= 1e-6 * abs(float(loss_ref)) + 1e-9
+
+
+def test_graph_replay_tracks_the_eager_engine_over_changing_cameras():
+    """TrainEngine(use_graph=True): the whole step captured once as a CUDA graph and replayed with a NEW camera / jitter seed /
+    learning-rate schedule per step (19 words of device-side step constants) against the eager engine on the same batches."""
+    from pointnerf2studio_b200 import RayBundle
+    from pointnerf2studio_b200.parallel import TrainEngine
+    from pointnerf2studio_b200.synth import make_camera
+    s, cloud, cam0, pix = _scene("config1")
+    pix = pix[:512]
+    W = of.FieldWeights.random(seed=13, scale=1.5)
+    gts = [torch.rand((len(pix), 3), generator=torch.Generator().manual_seed(20 + i)).cuda() for i in range(5)]
+    cams = [make_camera(azim_deg=30.0 + 17.0 * i, elev_deg=20.0 + 3.0 * i) for i in range(5)]
+    res = {}
+    for mode in ("eager", "graph"):
+        m = _make_model(cloud, "bf16", "plugin", SR=24, K=s["K"], P=s["P"], weights=W).train()
+        m.config.jitter = 0.3                       # the in-kernel jitter (seed = call counter) is what a graph replays
+        eng = TrainEngine(m, None, lr_fields=5e-3, lr_points=2e-2, lr_decay_iters=10, use_graph=(mode == "graph"))
+        losses = []
+        for i in range(5):
+            rb = RayBundle.for_camera(torch.from_numpy(cams[i].rays(pix)).cuda(), cams[i].origin, cams[i].R_c2w, cams[i].near, cams[i].far)
+            losses.append(float(eng.step(rb, gts[i]).detach()))
+        torch.cuda.synchronize()
+        if mode == "graph":
+            assert len(eng._graphs) == 1 and eng.steps == 5
+        with torch.no_grad():
+            m.eval()
+            img = m.get_outputs(RayBundle.for_camera(torch.from_numpy(cams[0].rays(pix)).cuda(), cams[0].origin, cams[0].R_c2w, 2.0, 6.0))
+        res[mode] = (losses, {n: p.detach().clone() for n, p in m.named_parameters() if p.requires_grad}, img["coarse_raycolor"].clone(),
+                     m.neural_points._jitter_calls)
+    (la, pa, ia, ja), (lb, pb, ib, jb) = res["eager"], res["graph"]
+    assert ja == jb                                  # the same jitter stream was consumed
+    assert len(set(round(l, 5) for l in la)) == 5    # five different batches
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 2e-3 * max(abs(x), 1e-3), (la, lb)
+    for n in pa:
+        d = (pa[n] - pb[n]).abs()
+        assert float(d.mean()) <= 3e-4 and float((d > 2e-3).float().mean()) <= 0.02, (n, float(d.mean()), float(d.max()))
+    assert float((ia - ib).abs().max()) <= 2e-2
