@@ -407,6 +407,19 @@ def bench_train(c, cam, steps, warmup):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed_steps(step_e2e, steps, c.flush, dist)
+    if engine._graphs:       # per-stage device times need eager launches: a few untimed steps outside the graph (diagnostic only)
+        engine.use_graph = False
+        native.Timers.enabled = True
+        native.Timers.spans = []
+        for _ in range(3):
+            step_dev()
+        torch.cuda.synchronize()
+        spans = native.Timers.collect()
+        native.Timers.enabled = False
+        engine.use_graph = True
+        n_span = 3
+    else:
+        n_span = steps
     # gradient exchange + Adam + gradient reset on their own: a few more steps with an event pair around TrainEngine.update()
     # (after a barrier, so that the wait for the slowest rank is not billed to it)
     engine.timing = []
@@ -418,7 +431,7 @@ def bench_train(c, cam, steps, warmup):
     ar_ms = statistics.median(a.elapsed_time(b) for a, b in engine.timing)
     engine.timing = None
     ms_total, ms_e2e, ar_ms = max_over_ranks([ms_total, ms_e2e, ar_ms], dist)
-    stage_ms = {k: sum(v) / steps for k, v in spans.items()}
+    stage_ms = {k: sum(v) / n_span for k, v in spans.items()}
     field_ms = stage_ms.get("render_fwd", 0.0) + stage_ms.get("render_bwd", 0.0)     # the two one-call launchers (pnerf_render_train_*)
     flops = 3.0 * (FIELD_FLOP_ROW * st["M"] + COLOR_FLOP_SAMPLE * st["S"])      # fwd + dgrad + wgrad
     ach = flops / (field_ms * 1e-3) / 1e12 if field_ms > 0 else 0.0

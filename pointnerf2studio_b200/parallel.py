@@ -360,15 +360,20 @@ class TrainEngine:
         c.consts.copy_(self._consts(ray_bundle, 1))
         c.consts[16:18] = 0.0
         keep_m, keep_v = self.m.clone(), self.v.clone()
+        # the capture stream differs from the stream the parameters' AccumulateGrad nodes were created on: expected here
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
                 eager()
         torch.cuda.current_stream().wait_stream(side)
+        from . import native
         c.graph = torch.cuda.CUDAGraph()
+        n0 = native.LAUNCHES["n"]
         with torch.cuda.graph(c.graph):
             c.loss = eager()
+        c.launches = native.LAUNCHES["n"] - n0          # kernels of one replay
         # warm-up and capture ran Adam's moment updates with real gradients: restore the state (the parameters did not move: lr 0)
         self.m.copy_(keep_m); self.v.copy_(keep_v)
         self.steps = steps0
@@ -389,6 +394,8 @@ class TrainEngine:
         c.gt.copy_(image, non_blocking=True)
         c.graph.replay()
         torch.autograd.graph.increment_version(self.params)
+        from . import native
+        native.LAUNCHES["n"] += c.launches
         return c.loss
 
     def step(self, ray_bundle, image):
