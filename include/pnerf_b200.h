@@ -123,6 +123,12 @@ int pnerf_gather_rays(const int* ray_index, int n_rays, int SR, int K, const int
 int pnerf_sample_compact(const uint8_t* sample_valid, int64_t n_slots, int* sample_ids, int* n_samples,
                          void* workspace, int64_t workspace_bytes, void* stream);
 int64_t pnerf_scan_workspace_bytes(int64_t n);
+/* The same list bucketed by neighbour count, for the tensor-core field kernels: class c (class_kp_h strictly descending powers of
+ * two, class_kp_h[0] >= K, e.g. {8, 4, 2}) holds, ascending, the slots whose number n of valid neighbours satisfies
+ * class_kp_h[c+1] < n <= class_kp_h[c] (the last class: 0 < n); sample_ids = the classes back to back, n_per_class [n_classes]
+ * (device) their sizes.  A class-c sample then occupies class_kp_h[c] MMA rows instead of K. */
+int pnerf_sample_compact_classes(const int* sample_pidx, int64_t n_slots, int K, int n_classes, const int* class_kp_h,
+                                 int* sample_ids, int* n_per_class, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- field networks (rows P, GA, W, E, M1, A, M2)
  * Replaces NeuralPoints.forward's gather (SU:190-209) and PointNerf.get_outputs' field math
@@ -205,6 +211,17 @@ int pnerf_field_backward_f32(const pnerf_points* pts_h, const pnerf_camera* cam_
 int64_t pnerf_tc_wpack_bytes(void);
 int pnerf_tc_pack_weights(const pnerf_mlp* mlp_h, void* wpack, void* stream);
 int64_t pnerf_field_tc_workspace_bytes(int64_t n_samples);
+/* The two kernels of pnerf_field_forward_tc on their own, for sample lists bucketed by neighbour count
+ * (pnerf_sample_compact_classes): the per-neighbour networks of `n_samples` samples with `rows_per_sample` (2, 4, 8, 16 or 32,
+ * >= every listed sample's neighbour count) MMA rows each, writing the aggregated features of sample i to position
+ * first_sample + i of `workspace` (512 B per sample, 128-sample tiles); then ONE colour-network launch over the whole list. */
+int pnerf_field_forward_tc_part(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const void* wpack,
+                                const pnerf_mode* mode_h, const float* dirs, const float* sample_loc, const int* sample_pidx,
+                                const int* sample_ids, int n_samples, int rows_per_sample, int first_sample, int SR, int K,
+                                float* sigma, void* workspace, int64_t workspace_bytes, void* stream);
+int pnerf_color_forward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const void* wpack,
+                           const pnerf_mode* mode_h, const float* dirs, const int* sample_ids, int n_samples, int SR, float* rgb,
+                           const void* workspace, int64_t workspace_bytes, void* stream);
 int pnerf_field_forward_tc(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const void* wpack,
                            const pnerf_mode* mode_h, const float* dirs, const float* sample_loc, const int* sample_pidx,
                            const int* sample_ids, int n_samples, int SR, int K, float* sigma, float* rgb, void* workspace,

@@ -100,6 +100,13 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p]),
     "pnerf_sample_compact": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                        C.c_void_p]),
+    "pnerf_sample_compact_classes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_int64, C.c_void_p]),
+    "pnerf_field_forward_tc_part": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.c_void_p, C.POINTER(Mode),
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pnerf_color_forward_tc": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.c_void_p, C.POINTER(Mode), C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pnerf_scan_workspace_bytes": (C.c_int64, [C.c_int64]),
     "pnerf_field_f32_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int]),
     "pnerf_field_forward_f32": (C.c_int, [C.POINTER(Points), C.POINTER(Camera), C.POINTER(Mlp), C.POINTER(Mode),

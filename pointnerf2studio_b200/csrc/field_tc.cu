@@ -72,7 +72,7 @@ constexpr int ENC_PARTS = PNERF_ENC_PARTS;       // threads per row in the encod
 constexpr int EPW = PNERF_EPW;                           // epilogue warps per slot: 4 (a warp drains all 256 columns of its 32 lanes) or 8 (128 each)
 constexpr int ENCW = 4 * ENC_PARTS;
 constexpr int NT = (ENCW + 2 * EPW + 2) * 32;    // encoder + 2 x EPW epilogue + producer + issuer warps
-constexpr int MAX_SPT = 16;                      // samples per tile at KP = 8
+constexpr int MAX_SPT = 64;                      // samples per tile at KP = 2
 
 // colour network
 constexpr int HC = 128;
@@ -116,6 +116,7 @@ struct FieldParams {
     const float* cam_dev;           // pnerf_camera.dev: per-step camera read at run time, or NULL
     int S, SR, K, n_tiles;          // S / n_tiles: host-side CAPACITY when S_dev is set (grid and workspace are sized from it)
     const int* S_dev;               // device-side number of valid samples (<= S), or NULL: the host does not know S and never syncs for it
+    int si0;                        // position of this launch's first sample in F (sample lists bucketed by neighbour count)
     float slope;
     int softplus, weight_conf;
     float* sigma;                   // (R*SR) by slot
@@ -389,6 +390,8 @@ __device__ __forceinline__ void butterfly(float* a, int lane) {
     if (KP == 32) { bfly_step<16, 32>(a, lane); bfly_step<8, 16>(a, lane); bfly_step<4, 8>(a, lane); bfly_step<2, 4>(a, lane); bfly_step<1, 2>(a, lane); }
     if (KP == 16) { bfly_step<8, 32>(a, lane); bfly_step<4, 16>(a, lane); bfly_step<2, 8>(a, lane); bfly_step<1, 4>(a, lane); }
     if (KP == 8) { bfly_step<4, 32>(a, lane); bfly_step<2, 16>(a, lane); bfly_step<1, 8>(a, lane); }
+    if (KP == 4) { bfly_step<2, 32>(a, lane); bfly_step<1, 16>(a, lane); }
+    if (KP == 2) { bfly_step<1, 32>(a, lane); }
 }
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
@@ -416,7 +419,10 @@ __device__ __forceinline__ void aggregate_chunk(const FieldParams& p, float (&v)
     if (slot >= 0) {
         const int c = c0 + gl * VPL;
         uint8_t* dst = p.F + (int64_t)(si / ROWS) * F_TILE_BYTES + (c >> 3) * SLAB + (si % ROWS) * 16 + (c & 7) * 2;
-        if (VPL == 4) {
+        if (VPL >= 8) {           // KP = 4 / 2: 8 / 16 columns per lane = one / two whole k-slab entries of the sample's row
+#pragma unroll
+            for (int q = 0; q < VPL / 8; q++) *reinterpret_cast<uint4*>(dst + q * SLAB) = pack8(v + 8 * q);
+        } else if (VPL == 4) {
             uint2 o; o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
             *reinterpret_cast<uint2*>(dst) = o;
         } else if (VPL == 2) {
@@ -434,7 +440,7 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
     constexpr int SPT = ROWS / KP;
     const int lane = threadIdx.x & 31, gl = lane % KP;
     const int sl = row / KP;
-    const int si = tile * SPT + sl;
+    const int si = p.si0 + tile * SPT + sl;
     const float w = meta.w[row];
     const int slot = meta.slot_id[sl];
     float dot = 0.f, dot1 = 0.f;     // even / odd columns of the density head
@@ -1029,8 +1035,8 @@ namespace pnerf {
 int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack, const pnerf_mode* mode,
                     const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S, const int* S_dev,
                     int SR, int K, float* sigma, float* rgb, void* F, uint8_t* save, float* save_w, float* save_raw, bool color,
-                    uint8_t* csave, cudaStream_t st) {
-    const int KP = K <= 8 ? 8 : (K <= 16 ? 16 : 32);
+                    uint8_t* csave, cudaStream_t st, int kp_override, int si0, bool field) {
+    const int KP = kp_override > 0 ? kp_override : (K <= 8 ? 8 : (K <= 16 ? 16 : 32));
     FieldParams p;
     p.xyz = pts->xyz; p.embed = pts->embed; p.color = pts->color; p.dir = pts->dir; p.conf = pts->conf;
     p.dirs = dirs; p.sample_loc = sample_loc; p.sample_pidx = sample_pidx; p.sample_ids = sample_ids;
@@ -1038,7 +1044,7 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     p.wa = mlp->wa; p.ba = mlp->ba;
     p.cam = make_cam(pts, cam);
     p.cam_dev = cam->dev;
-    p.S = S; p.S_dev = S_dev; p.SR = SR; p.K = K;
+    p.S = S; p.S_dev = S_dev; p.si0 = si0; p.SR = SR; p.K = K;
     const int spt = ROWS / KP;
     p.n_tiles = (S + spt - 1) / spt;
     p.slope = mode->lrelu_slope; p.softplus = mode->density_softplus; p.weight_conf = mode->weight_conf;
@@ -1065,9 +1071,19 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     }
     cudaEventRecord(g_tev[0], st);
 #endif
-    int rc;
-    if (save) rc = KP == 8 ? launch(field_tc_kernel<8, true>) : (KP == 16 ? launch(field_tc_kernel<16, true>) : launch(field_tc_kernel<32, true>));
-    else rc = KP == 8 ? launch(field_tc_kernel<8, false>) : (KP == 16 ? launch(field_tc_kernel<16, false>) : launch(field_tc_kernel<32, false>));
+    int rc = PNERF_OK;
+    if (!field) rc = PNERF_OK;
+    else if (save) rc = KP == 8 ? launch(field_tc_kernel<8, true>) : (KP == 16 ? launch(field_tc_kernel<16, true>) : (KP == 32 ? launch(field_tc_kernel<32, true>) : PNERF_ERR_ARG));
+    else {
+        switch (KP) {
+            case 2: rc = launch(field_tc_kernel<2, false>); break;
+            case 4: rc = launch(field_tc_kernel<4, false>); break;
+            case 8: rc = launch(field_tc_kernel<8, false>); break;
+            case 16: rc = launch(field_tc_kernel<16, false>); break;
+            case 32: rc = launch(field_tc_kernel<32, false>); break;
+            default: rc = PNERF_ERR_ARG;
+        }
+    }
     if (rc || !color) return rc;
 #ifdef PNERF_TC_TIMING
     cudaEventRecord(g_tev[1], st);
@@ -1106,5 +1122,29 @@ extern "C" int pnerf_field_forward_tc(const pnerf_points* pts, const pnerf_camer
     if (!workspace || workspace_bytes < pnerf_field_tc_workspace_bytes(S)) return PNERF_ERR_WORKSPACE;
     if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;   // lrelu(x) = max(x, slope x)
     return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, nullptr, SR, K, sigma, rgb, workspace,
-                           nullptr, nullptr, nullptr, true, nullptr, (cudaStream_t)stream);
+                           nullptr, nullptr, nullptr, true, nullptr, (cudaStream_t)stream, 0, 0, true);
+}
+
+extern "C" int pnerf_field_forward_tc_part(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack,
+                                           const pnerf_mode* mode, const float* dirs, const float* sample_loc, const int* sample_pidx,
+                                           const int* sample_ids, int S, int rows_per_sample, int first_sample, int SR, int K, float* sigma,
+                                           void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!pts || !cam || !mlp || !wpack || !mode || S < 0 || K <= 0 || K > 32 || SR <= 0 || first_sample < 0) return PNERF_ERR_ARG;
+    const int kp = rows_per_sample;
+    if (kp != 2 && kp != 4 && kp != 8 && kp != 16 && kp != 32) return PNERF_ERR_ARG;
+    if (S == 0) return PNERF_OK;
+    if (!workspace || workspace_bytes < pnerf_field_tc_workspace_bytes((int64_t)first_sample + S)) return PNERF_ERR_WORKSPACE;
+    if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;
+    return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, sample_loc, sample_pidx, sample_ids, S, nullptr, SR, K, sigma, nullptr, workspace,
+                           nullptr, nullptr, nullptr, false, nullptr, (cudaStream_t)stream, kp, first_sample, true);
+}
+
+extern "C" int pnerf_color_forward_tc(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack,
+                                      const pnerf_mode* mode, const float* dirs, const int* sample_ids, int S, int SR, float* rgb,
+                                      const void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!pts || !cam || !mlp || !wpack || !mode || S < 0 || SR <= 0) return PNERF_ERR_ARG;
+    if (S == 0) return PNERF_OK;
+    if (!workspace || !rgb || workspace_bytes < pnerf_field_tc_workspace_bytes(S)) return PNERF_ERR_WORKSPACE;
+    return field_tc_launch(pts, cam, mlp, wpack, mode, dirs, nullptr, nullptr, sample_ids, S, nullptr, SR, 8, nullptr, rgb, (void*)workspace,
+                           nullptr, nullptr, nullptr, true, nullptr, (cudaStream_t)stream, 0, 0, false);
 }

@@ -27,6 +27,6 @@ constexpr int64_t F_TILE_BYTES = (int64_t)32 * SLAB;                // 65 536
 int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pnerf_mlp* mlp, const void* wpack, const pnerf_mode* mode,
                     const float* dirs, const float* sample_loc, const int* sample_pidx, const int* sample_ids, int S, const int* S_dev,
                     int SR, int K, float* sigma, float* rgb, void* F, uint8_t* save, float* save_w, float* save_raw, bool color,
-                    uint8_t* csave, cudaStream_t st);
+                    uint8_t* csave, cudaStream_t st, int kp_override = 0, int si0 = 0, bool field = true);
 
 }  // namespace pnerf

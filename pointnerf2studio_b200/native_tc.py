@@ -41,24 +41,66 @@ def packed_weights(mlp_params, force: bool = False):
     return buf, mlp, params
 
 
-def field_forward_tc(cfg, q, dirs, pts, mlp, wpack, ids, S: int):
+def class_rows(K: int):
+    """Rows-per-sample classes for lists bucketed by neighbour count: the power of two >= K, then its halves down to 2."""
+    kp = 2
+    while kp < K:
+        kp *= 2
+    out = [kp]
+    while out[-1] > 2:
+        out.append(out[-1] // 2)
+    return out
+
+
+def compact_sample_classes(sample_pidx):
+    """Valid samples bucketed by neighbour count (csrc/scan.cu): -> (ids, per-class counts on the host, rows per sample of each class).
+    One host sync for the counts (the data-dependent sizes of the launches that follow)."""
+    lib = _lib.load()
+    R, SR, K = sample_pidx.shape
+    n = R * SR
+    dev = sample_pidx.device
+    kps = class_rows(K)
+    ids = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+    cnt = torch.empty((len(kps),), dtype=torch.int32, device=dev)
+    ws_bytes = lib.pnerf_scan_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib.pnerf_sample_compact_classes(_ptr(sample_pidx), n, K, len(kps), (C.c_int * len(kps))(*kps), _ptr(ids), _ptr(cnt), _ptr(ws),
+                                           ws_bytes, _stream()), "pnerf_sample_compact_classes")
+    LAUNCHES["n"] += 5 * len(kps)
+    return ids, [int(v) for v in cnt.tolist()], kps
+
+
+def field_forward_tc(cfg, q, dirs, pts, mlp, wpack, ids, counts, kps):
+    """Inference: per-neighbour networks class by class (a class-c sample occupies kps[c] MMA rows), then the colour network."""
     lib = _lib.load()
     R, SR, K = q.sample_pidx.shape
     dev = dirs.device
+    S = sum(counts)
     sigma = torch.zeros((R, SR), dtype=torch.float32, device=dev)
     rgb = torch.zeros((R, SR, 3), dtype=torch.float32, device=dev)
-    # the aggregated features between the two kernels cost 512 B per valid sample: the compact sample list is walked in pieces so
+    # the aggregated features between the two kernels cost 512 B per valid sample: the sample list is walked in pieces so
     # that a dense scene (up to R * SR samples) cannot ask for more than MAX_SAMPLES_PER_LAUNCH * 512 B of workspace
     piece = min(S, MAX_SAMPLES_PER_LAUNCH)
     ws_bytes = lib.pnerf_field_tc_workspace_bytes(piece)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    bounds = [0]
+    for c in counts:
+        bounds.append(bounds[-1] + c)
+    cam, mode = C.byref(cfg["camera"]), C.byref(cfg["mode"])
     with Timers.span("field"):
         for off in range(0, S, max(piece, 1)):
             n = min(piece, S - off)
-            check(lib.pnerf_field_forward_tc(C.byref(pts), C.byref(cfg["camera"]), C.byref(mlp), _ptr(wpack), C.byref(cfg["mode"]),
-                                             _ptr(dirs), _ptr(q.sample_loc), _ptr(q.sample_pidx), ids.data_ptr() + 4 * off, n, SR, K,
-                                             _ptr(sigma), _ptr(rgb), _ptr(ws), ws_bytes, _stream()), "pnerf_field_forward_tc")
-            LAUNCHES["n"] += 2
+            for ci, kp in enumerate(kps):                  # the part of class ci inside [off, off + n)
+                lo, hi = max(bounds[ci], off), min(bounds[ci + 1], off + n)
+                if hi <= lo:
+                    continue
+                check(lib.pnerf_field_forward_tc_part(C.byref(pts), cam, C.byref(mlp), _ptr(wpack), mode, _ptr(dirs), _ptr(q.sample_loc),
+                                                      _ptr(q.sample_pidx), ids.data_ptr() + 4 * lo, hi - lo, kp, lo - off, SR, K, _ptr(sigma),
+                                                      _ptr(ws), ws_bytes, _stream()), "pnerf_field_forward_tc_part")
+                LAUNCHES["n"] += 1
+            check(lib.pnerf_color_forward_tc(C.byref(pts), cam, C.byref(mlp), _ptr(wpack), mode, _ptr(dirs), ids.data_ptr() + 4 * off, n, SR,
+                                             _ptr(rgb), _ptr(ws), ws_bytes, _stream()), "pnerf_color_forward_tc")
+            LAUNCHES["n"] += 1
     return sigma, rgb
 
 
@@ -141,8 +183,8 @@ def render_tc(cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, mlp_params):
         return _RenderTC.apply(cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, *mlp_params)
     wpack, mlp, _ = packed_weights(mlp_params)
     pts = make_points(xyz.detach(), embed.detach(), color.detach(), dirn.detach(), conf.detach(), Rw2c)
-    ids, n_dev = native.compact_samples(q.sample_valid)
-    S = int(n_dev.item())
-    sigma, rgb = field_forward_tc(cfg, q, dirs, pts, mlp, wpack, ids, S)
-    cfg["last"] = {"sigma": sigma, "rgb": rgb, "n_samples": S}
+    with Timers.span("compact"):
+        ids, counts, kps = compact_sample_classes(q.sample_pidx)
+    sigma, rgb = field_forward_tc(cfg, q, dirs, pts, mlp, wpack, ids, counts, kps)
+    cfg["last"] = {"sigma": sigma, "rgb": rgb, "n_samples": sum(counts), "class_counts": counts, "class_rows": kps}
     return native.composite_forward(cfg, q, sigma, rgb)

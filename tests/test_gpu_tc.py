@@ -145,3 +145,29 @@ def test_tc_training_forward_backward_matches_fp32_autograd(flow, K):
         close(own[k].grad.cpu().numpy(), v.grad.numpy(), k, 2.5e-2, 0.99998)
         close(own[k].grad.cpu().numpy(), w32[k].numpy(), k + " (vs fp32 oracle)", 6e-2, 0.999)
     assert not bad, bad
+
+
+def test_sample_lists_bucketed_by_neighbour_count():
+    """pnerf_sample_compact_classes: class c holds, ascending, the slots with class_rows[c+1] < #neighbours <= class_rows[c]."""
+    from pointnerf2studio_b200 import native_tc
+    rng = np.random.default_rng(0)
+    for K in (8, 16, 3):
+        R, SR = 37, 24
+        cnt = rng.integers(0, K + 1, size=(R, SR))
+        cnt[rng.random((R, SR)) < 0.4] = 0
+        pidx = np.full((R, SR, K), -1, np.int32)
+        for r in range(R):
+            for s_ in range(SR):
+                pidx[r, s_, :cnt[r, s_]] = rng.integers(0, 1000, size=cnt[r, s_])
+        ids, counts, kps = native_tc.compact_sample_classes(torch.from_numpy(pidx).cuda())
+        assert kps == native_tc.class_rows(K) and kps[0] >= K and kps[-1] == 2
+        ids = ids.cpu().numpy()
+        flat = cnt.reshape(-1)
+        off = 0
+        for ci, kp in enumerate(kps):
+            lo = kps[ci + 1] if ci + 1 < len(kps) else 0
+            want = np.nonzero((flat > lo) & (flat <= kp))[0]
+            assert counts[ci] == len(want)
+            np.testing.assert_array_equal(ids[off:off + counts[ci]], want)
+            off += counts[ci]
+        assert off == int((flat > 0).sum())
