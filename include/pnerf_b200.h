@@ -105,7 +105,7 @@ int pnerf_coarse_t(float near_t, float far_t, float jitter, uint64_t seed, int R
  * are visited in (layer, ux, uy, uz, point index) order, the K kept are the K smallest by
  * (d2, visit order) and are emitted in that order; d2 = fma(dz,dz,fma(dy,dy,dx*dx)).
  * outputs: sample_pidx (R,SR,K) with -1 padding (every slot is written);
- *          sample_valid (R*SR) uint8: slot has >= 1 neighbour;
+ *          sample_valid (R*SR) uint8: the number of neighbours found for the slot (0 = none; every consumer tests it for != 0);
  *          stats (optional, 2 x uint64): voxel-table entries visited, candidate points examined. */
 int pnerf_query(const pnerf_grid_view* grid_h, const float* sample_loc, const int* sample_cnt, int R, int SR,
                 int K, int kernel_size0, float radius, int* sample_pidx, uint8_t* sample_valid,
@@ -127,7 +127,7 @@ int64_t pnerf_scan_workspace_bytes(int64_t n);
  * two, class_kp_h[0] >= K, e.g. {8, 4, 2}) holds, ascending, the slots whose number n of valid neighbours satisfies
  * class_kp_h[c+1] < n <= class_kp_h[c] (the last class: 0 < n); sample_ids = the classes back to back, n_per_class [n_classes]
  * (device) their sizes.  A class-c sample then occupies class_kp_h[c] MMA rows instead of K. */
-int pnerf_sample_compact_classes(const int* sample_pidx, int64_t n_slots, int K, int n_classes, const int* class_kp_h,
+int pnerf_sample_compact_classes(const uint8_t* sample_count /* pnerf_query's sample_valid */, int64_t n_slots, int K, int n_classes, const int* class_kp_h,
                                  int* sample_ids, int* n_per_class, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------- field networks (rows P, GA, W, E, M1, A, M2)

@@ -336,7 +336,10 @@ __global__ void __launch_bounds__(128, KMAX <= 8 ? PNERF_Q_MINB : (KMAX == 16 ? 
                 for (int i = 0; i < KMAX; i++)
                     if (i < K) out[i] = bidx[i];
             }
-            sample_valid[sid] = bidx[0] >= 0 ? 1 : 0;
+            int nv = 0;                      // number of neighbours found: the valid entries are the first ones of the list
+#pragma unroll
+            for (int i = 0; i < KMAX; i++) nv += (i < K && bidx[i] >= 0) ? 1 : 0;
+            sample_valid[sid] = (uint8_t)nv;
         }
     }
     if (stats) {

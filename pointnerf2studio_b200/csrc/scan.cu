@@ -132,24 +132,19 @@ __global__ void scatter_ids_kernel(const uint8_t* __restrict__ flags, const int*
 // Samples bucketed by neighbour count: class c holds the samples whose count n satisfies lo_c < n <= kp_c (kp = 2, 4, 8, ...): the
 // tensor-core field kernel then runs class c with kp_c rows per sample instead of K rows for everybody (16 % of the rows of the
 // render bench are padding at 8 rows per sample: 19 % of its samples have <= 4 neighbours).
-__global__ void class_flags_kernel(const int* __restrict__ pidx, int64_t n, int K, int lo, int hi, int* __restrict__ out) {
+__global__ void class_flags_kernel(const uint8_t* __restrict__ cnt, int64_t n, int lo, int hi, int* __restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    // valid neighbours are the first entries of a slot's list (the query emits them sorted, -1 padded)
-    int c = 0;
-    const int* p = pidx + i * K;
-    for (int k = 0; k < K; k++) c += p[k] >= 0 ? 1 : 0;
+    const int c = cnt[i];
     out[i] = (c > lo && c <= hi) ? 1 : 0;
 }
-__global__ void scatter_class_kernel(const int* __restrict__ pidx, const int* __restrict__ pos, int64_t n, int K, int lo, int hi, int cls,
+__global__ void scatter_class_kernel(const uint8_t* __restrict__ cnt, const int* __restrict__ pos, int64_t n, int lo, int hi, int cls,
                                      int* __restrict__ ids, int* __restrict__ counts) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         int base = 0;
         for (int c = 0; c < cls; c++) base += counts[c];          // totals of the classes before this one (final: earlier launches)
-        int c = 0;
-        const int* p = pidx + i * K;
-        for (int k = 0; k < K; k++) c += p[k] >= 0 ? 1 : 0;
+        const int c = cnt[i];
         if (c > lo && c <= hi) ids[base + pos[i]] = (int)i;
     }
     if (i == 0) counts[cls] = pos[n];
@@ -264,7 +259,7 @@ extern "C" int pnerf_sample_compact(const uint8_t* sample_valid, int64_t n_slots
     return PNERF_OK;
 }
 
-extern "C" int pnerf_sample_compact_classes(const int* sample_pidx, int64_t n_slots, int K, int n_classes, const int* class_kp_h,
+extern "C" int pnerf_sample_compact_classes(const uint8_t* sample_count, int64_t n_slots, int K, int n_classes, const int* class_kp_h,
                                             int* sample_ids, int* n_per_class, void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_slots < 0 || K <= 0 || n_classes < 1 || n_classes > 8 || !class_kp_h || !sample_ids || !n_per_class) return PNERF_ERR_ARG;
@@ -273,18 +268,18 @@ extern "C" int pnerf_sample_compact_classes(const int* sample_pidx, int64_t n_sl
     if (class_kp_h[0] < K) return PNERF_ERR_ARG;                                                            // the first class takes the fullest samples
     PNERF_CUDA(cudaMemsetAsync(n_per_class, 0, 4 * (size_t)n_classes, st));
     if (n_slots == 0) return PNERF_OK;
-    if (!sample_pidx || !workspace) return PNERF_ERR_ARG;
+    if (!sample_count || !workspace) return PNERF_ERR_ARG;
     int64_t pos_bytes = align_up((n_slots + 1) * 4, 256);
     if (workspace_bytes < pos_bytes + scan_workspace_bytes(n_slots)) return PNERF_ERR_WORKSPACE;
     int* pos = (int*)workspace;
     unsigned blocks = (unsigned)((n_slots + 255) / 256);
     for (int c = 0; c < n_classes; c++) {
         const int hi = c == 0 ? K : class_kp_h[c], lo = c + 1 < n_classes ? class_kp_h[c + 1] : 0;
-        class_flags_kernel<<<blocks, 256, 0, st>>>(sample_pidx, n_slots, K, lo, hi, pos);
+        class_flags_kernel<<<blocks, 256, 0, st>>>(sample_count, n_slots, lo, hi, pos);
         PNERF_LAUNCH_CHECK();
         int rc = exclusive_scan_i32(pos, pos, n_slots, true, (char*)workspace + pos_bytes, workspace_bytes - pos_bytes, st);
         if (rc) return rc;
-        scatter_class_kernel<<<blocks, 256, 0, st>>>(sample_pidx, pos, n_slots, K, lo, hi, c, sample_ids, n_per_class);
+        scatter_class_kernel<<<blocks, 256, 0, st>>>(sample_count, pos, n_slots, lo, hi, c, sample_ids, n_per_class);
         PNERF_LAUNCH_CHECK();
     }
     return PNERF_OK;

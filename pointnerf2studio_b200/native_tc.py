@@ -52,19 +52,18 @@ def class_rows(K: int):
     return out
 
 
-def compact_sample_classes(sample_pidx):
-    """Valid samples bucketed by neighbour count (csrc/scan.cu): -> (ids, per-class counts on the host, rows per sample of each class).
+def compact_sample_classes(sample_valid, K):
+    """Valid samples bucketed by neighbour count (pnerf_query's sample_valid holds the count; csrc/scan.cu): -> (ids, per-class counts on the host, rows per sample of each class).
     One host sync for the counts (the data-dependent sizes of the launches that follow)."""
     lib = _lib.load()
-    R, SR, K = sample_pidx.shape
-    n = R * SR
-    dev = sample_pidx.device
+    n = sample_valid.numel()
+    dev = sample_valid.device
     kps = class_rows(K)
     ids = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
     cnt = torch.empty((len(kps),), dtype=torch.int32, device=dev)
     ws_bytes = lib.pnerf_scan_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib.pnerf_sample_compact_classes(_ptr(sample_pidx), n, K, len(kps), (C.c_int * len(kps))(*kps), _ptr(ids), _ptr(cnt), _ptr(ws),
+    check(lib.pnerf_sample_compact_classes(_ptr(sample_valid, torch.uint8), n, K, len(kps), (C.c_int * len(kps))(*kps), _ptr(ids), _ptr(cnt), _ptr(ws),
                                            ws_bytes, _stream()), "pnerf_sample_compact_classes")
     LAUNCHES["n"] += 5 * len(kps)
     return ids, [int(v) for v in cnt.tolist()], kps
@@ -184,7 +183,7 @@ def render_tc(cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, mlp_params):
     wpack, mlp, _ = packed_weights(mlp_params)
     pts = make_points(xyz.detach(), embed.detach(), color.detach(), dirn.detach(), conf.detach(), Rw2c)
     with Timers.span("compact"):
-        ids, counts, kps = compact_sample_classes(q.sample_pidx)
+        ids, counts, kps = compact_sample_classes(q.sample_valid, q.sample_pidx.shape[2])
     sigma, rgb = field_forward_tc(cfg, q, dirs, pts, mlp, wpack, ids, counts, kps)
     cfg["last"] = {"sigma": sigma, "rgb": rgb, "n_samples": sum(counts), "class_counts": counts, "class_rows": kps}
     return native.composite_forward(cfg, q, sigma, rgb)

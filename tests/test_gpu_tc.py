@@ -83,7 +83,7 @@ def test_tc_sample_pieces_are_bit_identical(monkeypatch):
     rb = _bundle(cam, pix)
     with torch.no_grad():
         whole = m.get_outputs(rb)["coarse_raycolor"].clone()
-        S = int(m.last_query_dense().sample_valid.sum().item())
+        S = int((m.last_query_dense().sample_valid > 0).sum().item())
         assert S > 1000
         for piece in (1000, 128, S - 1):
             monkeypatch.setattr(native_tc, "MAX_SAMPLES_PER_LAUNCH", piece)
@@ -159,7 +159,7 @@ def test_sample_lists_bucketed_by_neighbour_count():
         for r in range(R):
             for s_ in range(SR):
                 pidx[r, s_, :cnt[r, s_]] = rng.integers(0, 1000, size=cnt[r, s_])
-        ids, counts, kps = native_tc.compact_sample_classes(torch.from_numpy(pidx).cuda())
+        ids, counts, kps = native_tc.compact_sample_classes(torch.from_numpy(cnt.astype(np.uint8)).cuda(), K)
         assert kps == native_tc.class_rows(K) and kps[0] >= K and kps[-1] == 2
         ids = ids.cpu().numpy()
         flat = cnt.reshape(-1)

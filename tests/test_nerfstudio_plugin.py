@@ -78,7 +78,8 @@ def test_pipeline_call_sequence_on_the_gpu(tmp_path):
     out = _run(f"""
         import nerfstudio_stub as S
         S.install()
-        import functools, torch
+        import functools, random, torch
+        torch.manual_seed(0); random.seed(0)
         from pointnerf2studio_b200 import nerfstudio_plugin as P
         from pointnerf2studio_b200.synth import make_cloud
         cloud = make_cloud(50000, seed=1241, radii=(0.11, 0.16, 0.2), P=12)
@@ -93,6 +94,8 @@ def test_pipeline_call_sequence_on_the_gpu(tmp_path):
         assert isinstance(pipe, P.PointNerfPipeline) and isinstance(pipe.datamanager, P.PointNerfDataManager)
         model = pipe.model
         assert model.collider is not None and model.num_train_data == 3
+        with torch.no_grad():          # a freshly initialised density head can sit entirely below its ReLU (sigma = 0, no gradient at all)
+            model.field_output_density.net.bias.fill_(5.0)
         opts = S.Optimizers(spec.config.optimizers, pipe.get_param_groups())
         before = {{n: p.detach().clone() for n, p in model.named_parameters() if p.requires_grad}}
         pipe.train()

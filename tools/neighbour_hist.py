@@ -30,7 +30,7 @@ def main():
         print(f"  KP=4 tiles for the {le4} samples with <= 4 neighbours: {rows_split} rows ({100 * (rows_split - M) / rows_split:.1f} % padding, "
               f"{100 * (1 - rows_split / (8 * S)):.1f} % fewer rows)")
         # per-ray structure: samples per hit ray
-        per_ray = q.sample_valid.sum(1)
+        per_ray = (q.sample_valid > 0).sum(1)
         print("  valid samples per hit ray: mean %.1f, max %d" % (float(per_ray.float().mean()), int(per_ray.max())))
 
 

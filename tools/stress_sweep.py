@@ -43,7 +43,7 @@ def main():
             model.get_outputs(rb)                         # builds the grid, warms up
             q, _, _, _ = model.neural_points.query(rb, want_stats=True)
             torch.cuda.synchronize()
-            S, M = int(q.sample_valid.sum()), int((q.sample_pidx >= 0).sum())
+            S, M = int((q.sample_valid > 0).sum()), int((q.sample_pidx >= 0).sum())
             filled = int(q.sample_cnt.sum())
             vis, cand = [int(x) for x in q.stats.tolist()]
             del q
