@@ -132,22 +132,48 @@ __global__ void scatter_ids_kernel(const uint8_t* __restrict__ flags, const int*
 // Samples bucketed by neighbour count: class c holds the samples whose count n satisfies lo_c < n <= kp_c (kp = 2, 4, 8, ...): the
 // tensor-core field kernel then runs class c with kp_c rows per sample instead of K rows for everybody (16 % of the rows of the
 // render bench are padding at 8 rows per sample: 19 % of its samples have <= 4 neighbours).
-__global__ void class_flags_kernel(const uint8_t* __restrict__ cnt, int64_t n, int lo, int hi, int* __restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int c = cnt[i];
-    out[i] = (c > lo && c <= hi) ? 1 : 0;
+constexpr int kMaxClasses = 8;
+struct ClassBounds { int lo[kMaxClasses], hi[kMaxClasses]; int n; };
+__device__ __forceinline__ int class_of(const ClassBounds& b, int c) {
+    int cls = -1;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; k++)
+        if (k < b.n && c > b.lo[k] && c <= b.hi[k]) cls = k;
+    return cls;
 }
-__global__ void scatter_class_kernel(const uint8_t* __restrict__ cnt, const int* __restrict__ pos, int64_t n, int lo, int hi, int cls,
-                                     int* __restrict__ ids, int* __restrict__ counts) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        int base = 0;
-        for (int c = 0; c < cls; c++) base += counts[c];          // totals of the classes before this one (final: earlier launches)
-        const int c = cnt[i];
-        if (c > lo && c <= hi) ids[base + pos[i]] = (int)i;
+// pass 1: class sizes (one atomic per warp and class)
+__global__ void __launch_bounds__(256) class_count_kernel(const uint8_t* __restrict__ cnt, int64_t n, ClassBounds b, int* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + lane;
+        const int cls = i < n ? class_of(b, cnt[i]) : -1;
+        for (int k = 0; k < b.n; k++) {
+            const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+            if (lane == 0 && m) atomicAdd(counts + k, __popc(m));
+        }
     }
-    if (i == 0) counts[cls] = pos[n];
+}
+// pass 2: positions = class base + a per-class cursor advanced once per warp.  The order INSIDE a class is the order in which the
+// warps arrive (not ascending): the field kernels treat samples independently, so the result does not depend on it, and a warp's
+// 32 consecutive slots -- neighbouring samples of one ray, which share neural points -- stay together.
+__global__ void __launch_bounds__(256) class_scatter_kernel(const uint8_t* __restrict__ cnt, int64_t n, ClassBounds b, const int* __restrict__ counts,
+                                                            int* __restrict__ cursor, int* __restrict__ ids) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + lane;
+        const int cls = i < n ? class_of(b, cnt[i]) : -1;
+        int base = 0;
+        for (int k = 0; k < b.n; k++) {
+            const unsigned m = __ballot_sync(0xffffffffu, cls == k);
+            if (m) {
+                int start = 0;
+                if (lane == 0) start = atomicAdd(cursor + k, __popc(m));
+                start = __shfl_sync(0xffffffffu, start, 0);
+                if (cls == k) ids[base + start + __popc(m & ((1u << lane) - 1u))] = (int)i;
+            }
+            base += counts[k];
+        }
+    }
 }
 __global__ void ray_flags_kernel(const uint8_t* __restrict__ sample_valid, int R, int SR, int8_t* __restrict__ ray_mask,
                                  int* __restrict__ flag_i32) {
@@ -262,26 +288,24 @@ extern "C" int pnerf_sample_compact(const uint8_t* sample_valid, int64_t n_slots
 extern "C" int pnerf_sample_compact_classes(const uint8_t* sample_count, int64_t n_slots, int K, int n_classes, const int* class_kp_h,
                                             int* sample_ids, int* n_per_class, void* workspace, int64_t workspace_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_slots < 0 || K <= 0 || n_classes < 1 || n_classes > 8 || !class_kp_h || !sample_ids || !n_per_class) return PNERF_ERR_ARG;
+    if (n_slots < 0 || K <= 0 || n_classes < 1 || n_classes > kMaxClasses || !class_kp_h || !sample_ids || !n_per_class) return PNERF_ERR_ARG;
     for (int c = 0; c < n_classes; c++)
         if (class_kp_h[c] < 1 || (c > 0 && class_kp_h[c] >= class_kp_h[c - 1])) return PNERF_ERR_ARG;      // strictly descending
     if (class_kp_h[0] < K) return PNERF_ERR_ARG;                                                            // the first class takes the fullest samples
     PNERF_CUDA(cudaMemsetAsync(n_per_class, 0, 4 * (size_t)n_classes, st));
     if (n_slots == 0) return PNERF_OK;
-    if (!sample_count || !workspace) return PNERF_ERR_ARG;
-    int64_t pos_bytes = align_up((n_slots + 1) * 4, 256);
-    if (workspace_bytes < pos_bytes + scan_workspace_bytes(n_slots)) return PNERF_ERR_WORKSPACE;
-    int* pos = (int*)workspace;
-    unsigned blocks = (unsigned)((n_slots + 255) / 256);
-    for (int c = 0; c < n_classes; c++) {
-        const int hi = c == 0 ? K : class_kp_h[c], lo = c + 1 < n_classes ? class_kp_h[c + 1] : 0;
-        class_flags_kernel<<<blocks, 256, 0, st>>>(sample_count, n_slots, lo, hi, pos);
-        PNERF_LAUNCH_CHECK();
-        int rc = exclusive_scan_i32(pos, pos, n_slots, true, (char*)workspace + pos_bytes, workspace_bytes - pos_bytes, st);
-        if (rc) return rc;
-        scatter_class_kernel<<<blocks, 256, 0, st>>>(sample_count, pos, n_slots, lo, hi, c, sample_ids, n_per_class);
-        PNERF_LAUNCH_CHECK();
-    }
+    if (!sample_count || !workspace || workspace_bytes < 256) return PNERF_ERR_ARG;
+    ClassBounds b;
+    b.n = n_classes;
+    for (int c = 0; c < n_classes; c++) { b.hi[c] = c == 0 ? K : class_kp_h[c]; b.lo[c] = c + 1 < n_classes ? class_kp_h[c + 1] : 0; }
+    int* cursor = (int*)workspace;
+    PNERF_CUDA(cudaMemsetAsync(cursor, 0, 4 * kMaxClasses, st));
+    const int64_t want = (n_slots + 255) / 256;
+    const unsigned blocks = (unsigned)(want > (int64_t)kSMs * 16 ? (int64_t)kSMs * 16 : want);
+    class_count_kernel<<<blocks, 256, 0, st>>>(sample_count, n_slots, b, n_per_class);
+    PNERF_LAUNCH_CHECK();
+    class_scatter_kernel<<<blocks, 256, 0, st>>>(sample_count, n_slots, b, n_per_class, cursor, sample_ids);
+    PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }
 
