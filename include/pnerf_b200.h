@@ -126,9 +126,8 @@ int64_t pnerf_scan_workspace_bytes(int64_t n);
 /* The same list bucketed by neighbour count, for the tensor-core field kernels: class c (class_kp_h strictly descending powers of
  * two, class_kp_h[0] >= K, e.g. {8, 4, 2}) holds the slots whose number n of valid neighbours satisfies
  * class_kp_h[c+1] < n <= class_kp_h[c] (the last class: 0 < n); sample_ids = the classes back to back, n_per_class [n_classes]
- * (device) their sizes.  A class-c sample then occupies class_kp_h[c] MMA rows instead of K.  Inside a class the slots are NOT
- * sorted (two passes with warp-aggregated atomics instead of three scans over all R*SR slots; runs of up to 32 consecutive slots
- * stay together): samples are independent, so no result depends on the order.  workspace: >= 256 bytes. */
+ * (device) their sizes, each class ascending.  A class-c sample then occupies class_kp_h[c] MMA rows instead of K.
+ * workspace: pnerf_scan_workspace_bytes(n_slots) bytes is enough. */
 int pnerf_sample_compact_classes(const uint8_t* sample_count /* pnerf_query's sample_valid */, int64_t n_slots, int K, int n_classes, const int* class_kp_h,
                                  int* sample_ids, int* n_per_class, void* workspace, int64_t workspace_bytes, void* stream);
 

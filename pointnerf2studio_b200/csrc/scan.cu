@@ -141,35 +141,36 @@ __device__ __forceinline__ int class_of(const ClassBounds& b, int c) {
         if (k < b.n && c > b.lo[k] && c <= b.hi[k]) cls = k;
     return cls;
 }
-// Both passes walk the slots in tiles of 256 (one per block iteration) and touch the global counters ONCE per tile and class
-// (a per-warp atomic on three hot addresses serialised 800 k atomics: 0.35 ms per pass on the render bench).
-// pass 1: class sizes
-__global__ void __launch_bounds__(256) class_count_kernel(const uint8_t* __restrict__ cnt, int64_t n, ClassBounds b, int* __restrict__ counts) {
+// Three phases over tiles of 256 slots: per-tile class counts -> exclusive scan of each class's tile counts (n_slots / 256 entries,
+// not n_slots) -> scatter with the tile bases.  Deterministic, ascending inside every class (neighbouring samples of a ray, which
+// share neural points, stay neighbours: an arrival-ordered variant with atomics cost the field kernels 2 % of their time).
+__global__ void __launch_bounds__(256) class_tile_count_kernel(const uint8_t* __restrict__ cnt, int64_t n, ClassBounds b, int64_t n_tiles,
+                                                               int* __restrict__ tile_counts /* [class][n_tiles + 1] */) {
     __shared__ int s_tot[kMaxClasses];
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x < kMaxClasses) s_tot[threadIdx.x] = 0;
-    __syncthreads();
-    for (int64_t i0 = (int64_t)blockIdx.x * 256; i0 < n; i0 += (int64_t)gridDim.x * 256) {
-        const int64_t i = i0 + threadIdx.x;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        if (threadIdx.x < kMaxClasses) s_tot[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t i = t * 256 + threadIdx.x;
         const int cls = i < n ? class_of(b, cnt[i]) : -1;
         for (int k = 0; k < b.n; k++) {
             const unsigned m = __ballot_sync(0xffffffffu, cls == k);
             if (lane == 0 && m) atomicAdd(&s_tot[k], __popc(m));
         }
+        __syncthreads();
+        if (threadIdx.x < b.n) tile_counts[(int64_t)threadIdx.x * (n_tiles + 1) + t] = s_tot[threadIdx.x];
+        __syncthreads();
     }
-    __syncthreads();
-    if (threadIdx.x < b.n && s_tot[threadIdx.x]) atomicAdd(counts + threadIdx.x, s_tot[threadIdx.x]);
 }
-// pass 2: position = class base + the tile's share of the class cursor + rank inside the tile.  The order INSIDE a class is the
-// order in which the tiles arrive (ascending within a tile): the field kernels treat samples independently, so no result depends on
-// it, and neighbouring samples of a ray -- which share neural points -- stay together.
-__global__ void __launch_bounds__(256) class_scatter_kernel(const uint8_t* __restrict__ cnt, int64_t n, ClassBounds b, const int* __restrict__ counts,
-                                                            int* __restrict__ cursor, int* __restrict__ ids) {
+__global__ void __launch_bounds__(256) class_tile_scatter_kernel(const uint8_t* __restrict__ cnt, int64_t n, ClassBounds b, int64_t n_tiles,
+                                                                 const int* __restrict__ tile_pos /* scanned, [class][n_tiles + 1] */,
+                                                                 int* __restrict__ ids, int* __restrict__ counts) {
     __shared__ int s_w[8][kMaxClasses];      // per warp and class: count, then exclusive offset inside the tile
     __shared__ int s_base[kMaxClasses];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t i0 = (int64_t)blockIdx.x * 256; i0 < n; i0 += (int64_t)gridDim.x * 256) {
-        const int64_t i = i0 + threadIdx.x;
+    if (blockIdx.x == 0 && threadIdx.x < b.n) counts[threadIdx.x] = tile_pos[(int64_t)threadIdx.x * (n_tiles + 1) + n_tiles];
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t i = t * 256 + threadIdx.x;
         const int cls = i < n ? class_of(b, cnt[i]) : -1;
         unsigned mine = 0;
         for (int k = 0; k < b.n; k++) {
@@ -182,8 +183,8 @@ __global__ void __launch_bounds__(256) class_scatter_kernel(const uint8_t* __res
             const int k = threadIdx.x;
             int tot = 0, base = 0;
             for (int w = 0; w < 8; w++) { const int c = s_w[w][k]; s_w[w][k] = tot; tot += c; }
-            for (int c = 0; c < k; c++) base += counts[c];
-            s_base[k] = base + (tot ? atomicAdd(cursor + k, tot) : 0);
+            for (int c = 0; c < k; c++) base += tile_pos[(int64_t)c * (n_tiles + 1) + n_tiles];     // sizes of the classes before this one
+            s_base[k] = base + tile_pos[(int64_t)k * (n_tiles + 1) + t];
         }
         __syncthreads();
         if (cls >= 0) ids[s_base[cls] + s_w[warp][cls] + __popc(mine & ((1u << lane) - 1u))] = (int)i;
@@ -309,17 +310,23 @@ extern "C" int pnerf_sample_compact_classes(const uint8_t* sample_count, int64_t
     if (class_kp_h[0] < K) return PNERF_ERR_ARG;                                                            // the first class takes the fullest samples
     PNERF_CUDA(cudaMemsetAsync(n_per_class, 0, 4 * (size_t)n_classes, st));
     if (n_slots == 0) return PNERF_OK;
-    if (!sample_count || !workspace || workspace_bytes < 256) return PNERF_ERR_ARG;
+    if (!sample_count || !workspace) return PNERF_ERR_ARG;
     ClassBounds b;
     b.n = n_classes;
     for (int c = 0; c < n_classes; c++) { b.hi[c] = c == 0 ? K : class_kp_h[c]; b.lo[c] = c + 1 < n_classes ? class_kp_h[c + 1] : 0; }
-    int* cursor = (int*)workspace;
-    PNERF_CUDA(cudaMemsetAsync(cursor, 0, 4 * kMaxClasses, st));
-    const int64_t want = (n_slots + 255) / 256;
-    const unsigned blocks = (unsigned)(want > (int64_t)kSMs * 16 ? (int64_t)kSMs * 16 : want);
-    class_count_kernel<<<blocks, 256, 0, st>>>(sample_count, n_slots, b, n_per_class);
+    const int64_t n_tiles = (n_slots + 255) / 256;
+    const int64_t tc_bytes = align_up((int64_t)n_classes * (n_tiles + 1) * 4, 256);
+    if (workspace_bytes < tc_bytes + scan_workspace_bytes(n_tiles + 1)) return PNERF_ERR_WORKSPACE;
+    int* tile_counts = (int*)workspace;
+    const unsigned blocks = (unsigned)(n_tiles > (int64_t)kSMs * 32 ? (int64_t)kSMs * 32 : n_tiles);
+    class_tile_count_kernel<<<blocks, 256, 0, st>>>(sample_count, n_slots, b, n_tiles, tile_counts);
     PNERF_LAUNCH_CHECK();
-    class_scatter_kernel<<<blocks, 256, 0, st>>>(sample_count, n_slots, b, n_per_class, cursor, sample_ids);
+    for (int c = 0; c < n_classes; c++) {
+        int* tc = tile_counts + (int64_t)c * (n_tiles + 1);
+        int rc = exclusive_scan_i32(tc, tc, n_tiles, true, (char*)workspace + tc_bytes, workspace_bytes - tc_bytes, st);
+        if (rc) return rc;
+    }
+    class_tile_scatter_kernel<<<blocks, 256, 0, st>>>(sample_count, n_slots, b, n_tiles, tile_counts, sample_ids, n_per_class);
     PNERF_LAUNCH_CHECK();
     return PNERF_OK;
 }

@@ -148,7 +148,7 @@ def test_tc_training_forward_backward_matches_fp32_autograd(flow, K):
 
 
 def test_sample_lists_bucketed_by_neighbour_count():
-    """pnerf_sample_compact_classes: class c holds (in any order) the slots with class_rows[c+1] < #neighbours <= class_rows[c]."""
+    """pnerf_sample_compact_classes: class c holds, ascending, the slots with class_rows[c+1] < #neighbours <= class_rows[c]."""
     from pointnerf2studio_b200 import native_tc
     rng = np.random.default_rng(0)
     for K in (8, 16, 3):
@@ -168,6 +168,6 @@ def test_sample_lists_bucketed_by_neighbour_count():
             lo = kps[ci + 1] if ci + 1 < len(kps) else 0
             want = np.nonzero((flat > lo) & (flat <= kp))[0]
             assert counts[ci] == len(want)
-            np.testing.assert_array_equal(np.sort(ids[off:off + counts[ci]]), want)
+            np.testing.assert_array_equal(ids[off:off + counts[ci]], want)
             off += counts[ci]
         assert off == int((flat > 0).sum())
