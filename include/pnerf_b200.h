@@ -383,6 +383,10 @@ typedef struct {
     /* optional DEVICE array of 3 floats {lr[0] / bias_correction1, lr[1] / bias_correction1, 1 / sqrt(bias_correction2)} read at
      * run time instead of the values derived from lr / step above (CUDA-graph replay with a moving schedule) */
     const float* hyper_dev;
+    /* optional NVLS multicast addresses of the SAME gradient / parameter buffers (one virtual address that reaches every rank's
+     * copy through the NVSwitch): the gradient sum then is one multimem.ld_reduce per 16 bytes (reduced inside the switch) and the
+     * parameter broadcast one multimem.st -- a GPU's links carry 2/world of the flat size instead of 2 (world-1)/world.  Both or none. */
+    const float* mc_g; float* mc_p;
 } pnerf_dp_adam;
 int pnerf_dp_adam_step(const pnerf_dp_adam* h, float beta1, float beta2, float eps, float grad_scale, void* stream);
 

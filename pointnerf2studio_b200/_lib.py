@@ -56,7 +56,7 @@ class AdamSeg(C.Structure):
 
 class DpAdam(C.Structure):
     _fields_ = [("p", C.c_void_p * 8), ("g", C.c_void_p * 8), ("m", C.c_void_p), ("v", C.c_void_p), ("lo", C.c_int64), ("hi", C.c_int64),
-                ("boundary", C.c_int64), ("step", C.c_int64), ("lr", C.c_float * 2), ("world", C.c_int), ("rank", C.c_int), ("hyper_dev", C.c_void_p)]
+                ("boundary", C.c_int64), ("step", C.c_int64), ("lr", C.c_float * 2), ("world", C.c_int), ("rank", C.c_int), ("hyper_dev", C.c_void_p), ("mc_g", C.c_void_p), ("mc_p", C.c_void_p)]
 
 
 class RenderBuffers(C.Structure):

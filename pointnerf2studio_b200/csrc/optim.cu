@@ -60,8 +60,20 @@ struct DpArgs {
     int64_t lo, hi, boundary;
     float lr_c[2], inv_bc2_sqrt;
     const float* hyper_dev;          // {lr_c[0], lr_c[1], inv_bc2_sqrt} in device memory (graph replay), or NULL
+    const float* mc_g; float* mc_p;  // NVLS multicast addresses of the gradient / parameter buffers (all ranks at once), or NULL
     int world, me;
 };
+
+// NVSwitch multicast ("multimem") forms: ONE load returns the sum over every rank's copy, reduced inside the switch, and ONE store
+// lands in every rank's copy -- the links of a GPU carry 2 x 1/world of the flat size instead of 2 x (world-1)/world.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* addr) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st(float* addr, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 template <int W>
 __global__ void __launch_bounds__(512) dp_adam_kernel(const DpArgs a, float omb1, float b2, float omb2, float eps, float gscale) {
@@ -71,12 +83,17 @@ __global__ void __launch_bounds__(512) dp_adam_kernel(const DpArgs a, float omb1
     const float ibc2 = a.hyper_dev ? __ldg(a.hyper_dev + 2) : a.inv_bc2_sqrt;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const int64_t e = a.lo + 4 * i;
-        float4 gs[W];
+        float4 g;
+        if (W > 1 && a.mc_g) {
+            g = multimem_ld_reduce_add(a.mc_g + e);
+        } else {
+            float4 gs[W];
 #pragma unroll
-        for (int w = 0; w < W; w++) gs[w] = __ldcs(reinterpret_cast<const float4*>(a.g[w] + e));       // all loads in flight before the first add
-        float4 g = gs[0];
+            for (int w = 0; w < W; w++) gs[w] = __ldcs(reinterpret_cast<const float4*>(a.g[w] + e));   // all loads in flight before the first add
+            g = gs[0];
 #pragma unroll
-        for (int w = 1; w < W; w++) { g.x += gs[w].x; g.y += gs[w].y; g.z += gs[w].z; g.w += gs[w].w; }
+            for (int w = 1; w < W; w++) { g.x += gs[w].x; g.y += gs[w].y; g.z += gs[w].z; g.w += gs[w].w; }
+        }
         g.x *= gscale; g.y *= gscale; g.z *= gscale; g.w *= gscale;
         float4 p = *reinterpret_cast<const float4*>(a.p[a.me] + e);
         float4 m = reinterpret_cast<float4*>(a.m)[i], v = reinterpret_cast<float4*>(a.v)[i];
@@ -88,8 +105,12 @@ __global__ void __launch_bounds__(512) dp_adam_kernel(const DpArgs a, float omb1
         adam1(p.w, g.w, m.w, v.w, l3, omb1, b2, omb2, eps, ibc2);
         reinterpret_cast<float4*>(a.m)[i] = m;
         reinterpret_cast<float4*>(a.v)[i] = v;
+        if (W > 1 && a.mc_p) {
+            multimem_st(a.mc_p + e, p);
+        } else {
 #pragma unroll
-        for (int w = 0; w < W; w++) *reinterpret_cast<float4*>(a.p[w] + e) = p;
+            for (int w = 0; w < W; w++) *reinterpret_cast<float4*>(a.p[w] + e) = p;
+        }
     }
 }
 }  // namespace
@@ -110,6 +131,8 @@ extern "C" int pnerf_dp_adam_step(const pnerf_dp_adam* h, float beta1, float bet
     }
     a.me = 0;
     a.hyper_dev = h->hyper_dev;
+    a.mc_g = h->mc_g; a.mc_p = h->mc_p;
+    if ((a.mc_g == nullptr) != (a.mc_p == nullptr) || (((uintptr_t)a.mc_g | (uintptr_t)a.mc_p) & 15)) return PNERF_ERR_ARG;
     a.m = h->m; a.v = h->v; a.lo = h->lo; a.hi = h->hi; a.boundary = h->boundary; a.world = h->world;
     const double bc1 = 1.0 - pow((double)beta1, (double)h->step), bc2 = 1.0 - pow((double)beta2, (double)h->step);
     a.lr_c[0] = (float)(h->lr[0] / bc1); a.lr_c[1] = (float)(h->lr[1] / bc1); a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));

@@ -175,7 +175,8 @@ class TrainEngine:
 
       "p2p"   (default at world > 1 when torch's symmetric memory is available): P and G are peer-mapped on every rank and ONE
               kernel (pnerf_dp_adam_step) does reduce-scatter + Adam + all-gather over NVLink between two device-side barriers;
-              the Adam moments are sharded (rank r keeps them for its 1/world slice only).
+              the Adam moments are sharded (rank r keeps them for its 1/world slice only).  With NVLS multicast addresses
+              (NVSwitch) the sum is one multimem.ld_reduce and the broadcast one multimem.st per 16 bytes.
       "nccl"  one in-place NCCL all-reduce per bucket -- the point gradients start on a side stream as soon as the backward has
               scattered them (under the weight-gradient GEMMs), the confidence + MLP bucket follows -- then the same fused Adam
               kernel runs replicated on every rank.  This is DDP's data movement.
@@ -194,6 +195,7 @@ class TrainEngine:
         self.betas, self.eps, self.steps = betas, float(eps), 0
         self.timing = None           # set to a list to collect (start, end) CUDA-event pairs around update()
         self.use_graph = bool(use_graph)
+        self.use_multicast = os.environ.get("PNERF_DP_MULTICAST", "1") != "0"
         self._graphs = {}            # number of rays -> captured step
         self._lib = _lib.load()
         npnts = model.neural_points
@@ -278,6 +280,8 @@ class TrainEngine:
             for w in range(W):
                 a.p[w], a.g[w] = self._hdl_p.buffer_ptrs[w], self._hdl_g.buffer_ptrs[w]
             a.world, a.rank = W, self.rank
+            if self.use_multicast and self._hdl_p.multicast_ptr and self._hdl_g.multicast_ptr:
+                a.mc_p, a.mc_g = self._hdl_p.multicast_ptr, self._hdl_g.multicast_ptr     # NVLS: reduce / broadcast inside the switch
             self._hdl_g.barrier()                     # every rank's gradients are complete
         else:
             if self.exchange == "nccl":
