@@ -243,8 +243,11 @@ class TrainEngine:
         self.v = torch.zeros(hi - lo, dtype=torch.float32, device=dev)
         self._ev = torch.cuda.Event()
         self._comm = torch.cuda.Stream(device=dev) if exchange == "nccl" else None
+        self._side = torch.cuda.Stream(device=dev) if exchange == "p2p" else None
+        self.overlap = os.environ.get("PNERF_DP_OVERLAP", "1") != "0"
+        self._backward_ran = False
         self._ev.record()
-        model.set_grad_sink(self.G[:self.boundary], self.G[self.boundary:self.total], self._ev.cuda_event if exchange == "nccl" else 0)
+        model.set_grad_sink(self.G[:self.boundary], self.G[self.boundary:self.total], self._ev.cuda_event if exchange in ("nccl", "p2p") else 0)
         if exchange == "p2p":
             self._hdl_p.barrier()
 
@@ -260,15 +263,30 @@ class TrainEngine:
         f = pow(self.decay[0], self.steps / self.decay[1])
         return self.lr0[0] * f, self.lr0[1] * f
 
-    def backward_and_update(self, loss: torch.Tensor):
+    def backward_and_update(self, loss: torch.Tensor, hyper_dev=None):
         loss.backward()
-        self.update()
+        self._backward_ran = True          # the event inside the backward was recorded for THIS step: the early exchange may wait on it
+        self.update(hyper_dev)
+
+    def _adam(self, a, lo, hi, lr_p, lr_f, hyper_dev):
+        """One pnerf_dp_adam_step launch over the flat elements [lo, hi) of this rank's slice."""
+        import ctypes as C
+        from . import _lib
+        if hi <= lo:
+            return
+        a.m, a.v = self.m.data_ptr() + 4 * (lo - self.lo), self.v.data_ptr() + 4 * (lo - self.lo)
+        a.lo, a.hi, a.boundary, a.step = lo, hi, self.boundary, self.steps
+        a.lr = (C.c_float * 2)(lr_p, lr_f)
+        if hyper_dev is not None:
+            a.hyper_dev = hyper_dev.data_ptr()
+        _lib.check(self._lib.pnerf_dp_adam_step(C.byref(a), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                                                C.c_float(1.0 / self.world), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   "pnerf_dp_adam_step")
 
     def update(self, hyper_dev=None):
         """Gradient exchange + Adam + gradient reset, all enqueued on the current stream (nothing blocks the host).
         hyper_dev: device tensor {lr_points / bc1, lr_fields / bc1, 1 / sqrt(bc2)} read by the kernel at run time (graph replay)."""
-        import ctypes as C
-        from . import _lib
+        from . import _lib, native
         lr_p, lr_f = self.lrs()
         self.steps += 1
         if self.timing is not None:
@@ -276,17 +294,32 @@ class TrainEngine:
             t0.record()
         a = _lib.DpAdam()
         W = self.world
+        n_early = (self.N * 38) // 4 * 4           # embedding / colour / dir gradients: complete at the event recorded inside the backward
         if self.exchange == "p2p":
             for w in range(W):
                 a.p[w], a.g[w] = self._hdl_p.buffer_ptrs[w], self._hdl_g.buffer_ptrs[w]
             a.world, a.rank = W, self.rank
             if self.use_multicast and self._hdl_p.multicast_ptr and self._hdl_g.multicast_ptr:
                 a.mc_p, a.mc_g = self._hdl_p.multicast_ptr, self._hdl_g.multicast_ptr     # NVLS: reduce / broadcast inside the switch
-            self._hdl_g.barrier()                     # every rank's gradients are complete
+            cur = torch.cuda.current_stream()
+            mid = min(max(n_early, self.lo), self.hi)
+            if self.overlap and self._backward_ran:
+                # the bulk of the exchange (97 % of the bytes) starts on a side stream as soon as the backward has scattered the
+                # point gradients, under its weight-gradient GEMMs; the confidence + MLP tail follows the whole backward
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(self._ev)
+                    self._hdl_g.barrier(channel=1)
+                    self._adam(a, self.lo, mid, lr_p, lr_f, hyper_dev)
+                self._hdl_g.barrier(channel=0)            # every rank's backward is complete
+                self._adam(a, mid, self.hi, lr_p, lr_f, hyper_dev)
+                cur.wait_stream(self._side)
+            else:
+                self._hdl_g.barrier(channel=0)            # every rank's gradients are complete
+                self._adam(a, self.lo, self.hi, lr_p, lr_f, hyper_dev)
+            self._hdl_p.barrier(channel=0)                # every rank has read my gradients and written my parameters
         else:
             if self.exchange == "nccl":
                 cur = torch.cuda.current_stream()
-                n_early = self.N * 38                  # embedding / colour / dir: complete at the event recorded inside the backward
                 with torch.cuda.stream(self._comm):
                     self._comm.wait_event(self._ev)
                     w1 = self.dist.all_reduce(self.G[:n_early], async_op=True)
@@ -295,17 +328,9 @@ class TrainEngine:
                 cur.wait_stream(self._comm)
             a.p[0], a.g[0] = self.P.data_ptr(), self.G.data_ptr()
             a.world, a.rank = 1, 0
-        a.m, a.v = self.m.data_ptr(), self.v.data_ptr()
-        a.lo, a.hi, a.boundary, a.step = self.lo, self.hi, self.boundary, self.steps
-        if hyper_dev is not None:
-            a.hyper_dev = hyper_dev.data_ptr()
-        a.lr = (C.c_float * 2)(lr_p, lr_f)
-        _lib.check(self._lib.pnerf_dp_adam_step(C.byref(a), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
-                                                C.c_float(1.0 / W), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pnerf_dp_adam_step")
-        if self.exchange == "p2p":
-            self._hdl_p.barrier()                     # every rank has read my gradients and written my parameters
+            self._adam(a, self.lo, self.hi, lr_p, lr_f, hyper_dev)
+        self._backward_ran = False
         self.G.zero_()
-        from . import native
         native.LAUNCHES["n"] += 2
         torch.autograd.graph.increment_version(self.params)
         if self.timing is not None:
@@ -355,8 +380,7 @@ class TrainEngine:
         def eager():
             out = self.model.get_outputs(c.bundle)
             loss = sum(self.model.get_loss_dict(out, {"image": c.gt}).values())
-            loss.backward()
-            self.update(hyper)
+            self.backward_and_update(loss, hyper)
             return loss
 
         calls0, steps0 = self.model.neural_points._jitter_calls, self.steps
