@@ -78,8 +78,8 @@ constexpr int MAX_SPT = 64;                      // samples per tile at KP = 2
 constexpr int HC = 128;
 constexpr int C1_BYTES = (KIN_PAD / 8) * HC * 16;   // 73728: Wc1 128 x 288
 constexpr int C2_BYTES = (HC / 8) * HC * 16;        // 32768: Wc2 / Wc3 128 x 128
-constexpr int WPACK_FIELD_BYTES = (36 + 34 + 36 + 34) * HID * 16;          // 573440
-constexpr int WPACK_BYTES = WPACK_FIELD_BYTES + C1_BYTES + 2 * C2_BYTES;   // 696320
+constexpr int WPACK_FIELD_BYTES = (36 + 34 + 34 + 34) * HID * 16;          // 565248
+constexpr int WPACK_BYTES = WPACK_FIELD_BYTES + C1_BYTES + 2 * C2_BYTES;   // 688128
 
 struct Cam { float o[3]; float Rc[9]; float Rw[9]; };
 struct CamOR { float o[3]; float Rc[9]; };    // the per-step part (pnerf_camera.dev words 0..11)
@@ -485,9 +485,11 @@ __device__ __forceinline__ void epilogue_aggregate(const FieldParams& p, uint32_
     if (gl == 0 && slot >= 0) p.sigma[slot] = sg;                           // SM:344
 }
 
-__host__ __device__ constexpr int layer_slabs(int L) { return (L & 1) ? 34 : 36; }     // 8-wide k-slabs of the layer (K = 272 / 288)
+// 8-wide k-slabs of the layer: K = 288 for layer 1 (284 inputs + the bias column), K = 272 for the others -- layer 3's 263 inputs + its bias
+// column (264) fit 272 as well: one MMA less than the 288 it used to be padded to (1 of 70 per tile)
+__host__ __device__ constexpr int layer_slabs(int L) { return L == 0 ? 36 : 34; }
 __host__ __device__ constexpr int layer_chunks(int L) { return (void)L, 6; }            // 48-k chunks: 288 = 6 x 48, 272 = 5 x 48 + 32
-__host__ __device__ constexpr int layer_byte0(int L) { return HID * 16 * (L == 0 ? 0 : (L == 1 ? 36 : (L == 2 ? 70 : 106))); }
+__host__ __device__ constexpr int layer_byte0(int L) { return HID * 16 * (L == 0 ? 0 : (L == 1 ? 36 : (L == 2 ? 70 : 104))); }
 __host__ __device__ constexpr int chunk_slabs(int L, int c) {
     return layer_slabs(L) - CHUNK_SLABS * c < CHUNK_SLABS ? layer_slabs(L) - CHUNK_SLABS * c : CHUNK_SLABS;
 }
@@ -627,7 +629,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
                     if (L == 1) {   // layer-3 input columns 256..287: the 7 per-row extras and the constant 1 (bias column 263), then zeros
                         const RowSink<SAVE> A{reinterpret_cast<uint4*>(sm.A[s] + row * 16), reinterpret_cast<uint4*>(gsave + row * 16)};
                         A.put(32, sm.scratch[s].extras[row]);
-                        A.put(33, z); A.put(34, z); A.put(35, z);
+                        A.put(33, z);                               // K = 272: columns 264..271
+                        if (SAVE) { A.put(34, z); A.put(35, z); }   // the saved X3 tile keeps its 36-slab layout for the backward GEMMs
                     } else {        // layers 2 and 4 (K = 272): column 256 = 1 carries the bias, 257..271 = 0 (not part of the saved tile)
                         uint4* Arow = reinterpret_cast<uint4*>(sm.A[s] + row * 16);
                         Arow[32 * (SLAB / 16)] = make_uint4(0x00003F80u, 0u, 0u, 0u);
@@ -1013,7 +1016,7 @@ extern "C" int pnerf_tc_pack_weights(const pnerf_mlp* mlp, void* wpack, void* st
     PackJobs jobs;
     jobs.j[0] = {mlp->w1, 256, 284, 288, 0, 1, mlp->b1, BIAS_COL[0]};
     jobs.j[1] = {mlp->w2, 256, 256, 272, (int64_t)layer_byte0(1), 1, mlp->b2, BIAS_COL[1]};
-    jobs.j[2] = {mlp->w3, 256, 263, 288, (int64_t)layer_byte0(2), 1, mlp->b3, BIAS_COL[2]};
+    jobs.j[2] = {mlp->w3, 256, 263, 272, (int64_t)layer_byte0(2), 1, mlp->b3, BIAS_COL[2]};
     jobs.j[3] = {mlp->w4, 256, 256, 272, (int64_t)layer_byte0(3), 1, mlp->b4, BIAS_COL[3]};
     jobs.j[4] = {mlp->wc1, 128, 280, 288, (int64_t)WPACK_FIELD_BYTES, 2, nullptr, 0};
     jobs.j[5] = {mlp->wc2, 128, 128, 128, (int64_t)WPACK_FIELD_BYTES + C1_BYTES, 2, nullptr, 0};

@@ -195,7 +195,10 @@ class TrainEngine:
         self.betas, self.eps, self.steps = betas, float(eps), 0
         self.timing = None           # set to a list to collect (start, end) CUDA-event pairs around update()
         self.use_graph = bool(use_graph)
-        self.use_multicast = os.environ.get("PNERF_DP_MULTICAST", "1") != "0"
+        # NVLS multimem forms: measured on B200 / NVSwitch, update() of the 157 MB flat buffers: 8 GPUs 0.45 ms against 0.55 ms with plain
+        # peer loads / stores; 2 GPUs 0.50 against 0.32 ms (one peer: the switch adds a hop and saves nothing) -> on from 3 ranks up
+        mc = os.environ.get("PNERF_DP_MULTICAST")
+        self.use_multicast = (self.world > 2) if mc is None else (mc != "0")
         self._graphs = {}            # number of rays -> captured step
         self._lib = _lib.load()
         npnts = model.neural_points
@@ -244,7 +247,9 @@ class TrainEngine:
         self._ev = torch.cuda.Event()
         self._comm = torch.cuda.Stream(device=dev) if exchange == "nccl" else None
         self._side = torch.cuda.Stream(device=dev) if exchange == "p2p" else None
-        self.overlap = os.environ.get("PNERF_DP_OVERLAP", "1") != "0"
+        # starting the bulk of the exchange under the weight-gradient GEMMs was measured and LOST (2 GPUs: 1.84 against 1.66 ms per
+        # step): the exchange kernel and the spinning barrier take SMs from wgrad_tc_kernel (1 CTA per SM, all of TMEM).  Off by default.
+        self.overlap = os.environ.get("PNERF_DP_OVERLAP", "0") != "0"
         self._backward_ran = False
         self._ev.record()
         model.set_grad_sink(self.G[:self.boundary], self.G[self.boundary:self.total], self._ev.cuda_event if exchange in ("nccl", "p2p") else 0)

@@ -135,7 +135,7 @@ def test_argument_errors_are_return_codes_not_crashes():
     assert lib.pnerf_adam_step(None, 1, C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8), C.c_float(1.0), None) == ERR_ARG
     assert lib.pnerf_adam_step(None, 0, C.c_float(0.9), C.c_float(0.999), C.c_float(1e-8), C.c_float(1.0), None) == ERR_ARG
     assert lib.pnerf_hit_rays(None, 0, None, None, None, 0, None) == ERR_ARG
-    assert lib.pnerf_tc_wpack_bytes() == 573440 + 73728 + 2 * 32768
+    assert lib.pnerf_tc_wpack_bytes() == 565248 + 73728 + 2 * 32768
     assert lib.pnerf_field_tc_train_workspace_bytes(0, 8) > 0 and lib.pnerf_scan_workspace_bytes(1000) > 0
 
 
