@@ -228,6 +228,10 @@ __device__ __forceinline__ void list_insert(float (&bd2)[KMAX], int (&bidx)[KMAX
 // for every lane (a rejected or missing candidate carries d2 = +inf and changes nothing).  The nested per-run loops this
 // replaces executed sum_runs max_lane(len) iterations with a divergent 48-instruction insertion: 979 M warp instructions
 // for the render bench.
+// Tried in round 2 and dropped: skipping runs whose distance lower bound (gaps to the sample's voxel faces) is not below the K-th best
+// distance -- exact, and it removes ~20 % of the record loads, but the bound bookkeeping (a third shared-memory word per run, 20 B of
+// spills under the 56-register cap, a data-dependent loop instead of the precomputed trip count) cost more than the loads it saved:
+// 1.51 -> 1.72 ms on the render bench.
 // K <= 8: 62 registers leave 8 blocks (32 warps) per SM; capping at 56 (9 blocks) costs no spills and hides more of the record
 // loads' latency: -11 % on the render bench (tools/sweep_query.sh on one box: 1.65 / 1.46 / 1.53 ms at 8 / 9 / 10 blocks)
 #ifndef PNERF_Q_MINB
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(128, KMAX <= 8 ? PNERF_Q_MINB : (KMAX == 16 ? 
                                                      const int* __restrict__ sample_cnt, int R, int SR, int K, int layers,
                                                      float r2, int max_runs, int* __restrict__ sample_pidx,
                                                      uint8_t* __restrict__ sample_valid, unsigned long long* __restrict__ stats) {
-    extern __shared__ int s_runs[];                    // [max_runs][3][128]: start / length / distance bound of run j of thread t at (j*3 + {0,1,2})*128 + t
+    extern __shared__ int s_runs[];                    // [max_runs][2][128]: start / length of run j of thread t at (j*2 + {0,1})*128 + t
     const int lane = threadIdx.x & 31, t = threadIdx.x;
     const int cpr = (SR + 31) >> 5;                    // 32-slot chunks per ray
     const int64_t n_tasks = (int64_t)R * cpr;
@@ -266,31 +270,16 @@ __global__ void __launch_bounds__(128, KMAX <= 8 ? PNERF_Q_MINB : (KMAX == 16 ? 
                 searching = voxel_of(f, qx, qy, qz, vx, vy, vz);
             }
             int seen = 0;
-            // Lower bounds for pruning: a run (cells of one (x, y) row) lies at least gx(dx)^2 + gy(dy)^2 [+ gz^2] from the sample, where
-            // g is the distance from the sample to the face of its own voxel on that side plus whole voxels beyond it.  Once the list
-            // is full, a run whose bound is not below the K-th best distance cannot contribute (the insertion test is d2 < bd2[K-1])
-            // and is skipped without touching its records -- exact: `seen` already is >= K when the list is full.  The bounds are
-            // shrunk by a few ulps of the coordinates, since the voxel of a point comes from a rounded fp32 division.
-            const float fx0 = __fsub_rn(qx, __fmaf_rn((float)vx, f.sv[0], f.lo[0])), fy0 = __fsub_rn(qy, __fmaf_rn((float)vy, f.sv[1], f.lo[1]));
-            const float fz0 = __fsub_rn(qz, __fmaf_rn((float)vz, f.sv[2], f.lo[2]));
-            const float eps = 4e-6f * (1.f + fabsf(qx) + fabsf(qy) + fabsf(qz));
-            auto gap = [&](float below, float sv, int d) {      // distance to the cells d voxels away along one axis (0 for d == 0)
-                if (d == 0) return 0.f;
-                const float g = (d < 0 ? below : sv - below) + (float)(abs(d) - 1) * sv - eps;
-                return fmaxf(g, 0.f);
-            };
             for (int shell = 0; shell < layers; shell++) {
                 // ---- phase 1: this thread's runs of the shell, in visit order (ux, uy, uz)
-                int nr = 0;
+                int nr = 0, total = 0;
                 if (searching) {
                     for (int dx = -shell; dx <= shell; dx++) {
                         const int x = vx + dx;
                         if (x < 0 || x >= f.dim[0]) continue;
-                        const float gx = gap(fx0, f.sv[0], dx);
                         for (int dy = -shell; dy <= shell; dy++) {
                             const int y = vy + dy;
                             if (y < 0 || y >= f.dim[1]) continue;
-                            const float gy = gap(fy0, f.sv[1], dy);
                             const bool rim = max(abs(dx), abs(dy)) == shell;   // whole z range belongs to this shell
                             // rim rows: one run z in [vz-shell, vz+shell]; inner rows: two single cells z = vz -+ shell
                             const int parts = rim ? 1 : 2;
@@ -298,7 +287,6 @@ __global__ void __launch_bounds__(128, KMAX <= 8 ? PNERF_Q_MINB : (KMAX == 16 ? 
                                 int z0, z1;
                                 if (rim) { z0 = vz - shell; z1 = vz + shell; }
                                 else { z0 = z1 = part == 0 ? vz - shell : vz + shell; }
-                                const float gz = rim ? 0.f : gap(fz0, f.sv[2], part == 0 ? -shell : shell);
                                 z0 = max(z0, 0); z1 = min(z1, f.dim[2] - 1);
                                 if (z0 > z1) continue;
                                 const int c0 = cell_lin(f, x, y, z0);
@@ -306,40 +294,36 @@ __global__ void __launch_bounds__(128, KMAX <= 8 ? PNERF_Q_MINB : (KMAX == 16 ? 
                                 n_vis += (unsigned long long)(z1 - z0 + 1);
                                 n_cand += (unsigned long long)(b - a);
                                 if (b > a) {
-                                    s_runs[(nr * 3) * 128 + t] = a;
-                                    s_runs[(nr * 3 + 1) * 128 + t] = b - a;
-                                    s_runs[(nr * 3 + 2) * 128 + t] = __float_as_int(__fmaf_rn(gz, gz, __fmaf_rn(gy, gy, gx * gx)));
-                                    nr++;
+                                    s_runs[(nr * 2) * 128 + t] = a;
+                                    s_runs[(nr * 2 + 1) * 128 + t] = b - a;
+                                    nr++; total += b - a;
                                 }
                             }
                         }
                     }
                 }
                 // ---- phase 2: all candidate streams of the warp in lock step
-                int run = -1, i = 0, rem = 0;
-                auto next_run = [&]() {          // the next run of this thread's list that can still contribute
-                    for (;;) {
-                        run++;
-                        if (run >= nr) { rem = 0; return; }
-                        const int* e = s_runs + (run * 3) * 128 + t;
-                        if (__int_as_float(e[256]) >= bd2[KMAX - 1]) continue;
-                        i = e[0]; rem = e[128];
-                        return;
-                    }
-                };
-                next_run();
-                while (__any_sync(0xffffffffu, rem > 0)) {
+                const int trips = __reduce_max_sync(0xffffffffu, total);
+                int run = 0, i = 0, rem = 0;
+                if (nr > 0) { i = s_runs[t]; rem = s_runs[128 + t]; }
+                for (int it = 0; it < trips; it++) {
                     float d2 = INFINITY;
                     int idx = -1;
-                    if (rem > 0) {
+                    if (it < total) {
                         const float4 rec = __ldg(recs + i);
                         const float ex = __fsub_rn(rec.x, qx), ey = __fsub_rn(rec.y, qy), ez = __fsub_rn(rec.z, qz);
                         const float dd = __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));   // CU:271 as nvcc contracts it
                         if (r2 == 0.f || dd <= r2) { seen++; d2 = dd; idx = __float_as_int(rec.w) & 0x0fffffff; }
                         i++; rem--;
+                        if (rem == 0) {                          // next run of this thread's list
+                            run++;
+                            if (run < nr) {
+                                const int* e = s_runs + (run * 2) * 128 + t;
+                                i = e[0]; rem = e[128];
+                            }
+                        }
                     }
                     if (__any_sync(0xffffffffu, d2 < bd2[KMAX - 1])) list_insert<KMAX>(bd2, bidx, d2, idx);
-                    if (rem == 0 && run < nr) next_run();    // after the insertion: the bound the next run is tested against is current
                 }
                 if (seen >= K) searching = false;   // CU:300: this sample stops after the layer; the warp goes on for the others
                 if (!__any_sync(0xffffffffu, searching)) break;
@@ -458,7 +442,7 @@ extern "C" int pnerf_query(const pnerf_grid_view* g, const float* sample_loc, co
     cudaStream_t st = (cudaStream_t)stream;
     const float4* recs = (const float4*)g->recs;
     const int max_runs = layers == 1 ? 1 : (layers == 2 ? 10 : 34);     // runs of the largest shell: 1, 8 + 2, 16 + 18
-    const size_t smem = (size_t)max_runs * 3 * 128 * sizeof(int);
+    const size_t smem = (size_t)max_runs * 2 * 128 * sizeof(int);
 #define PNERF_LAUNCH_Q(KM) \
     query_kernel<KM><<<blocks, 128, smem, st>>>(f, g->cell_start, recs, sample_loc, sample_cnt, R, SR, K, layers, r2, max_runs, sample_pidx, sample_valid, stats)
     if (K <= 4) PNERF_LAUNCH_Q(4);
