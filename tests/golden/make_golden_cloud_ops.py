@@ -89,6 +89,29 @@ def main():
         out[f"probe_{tag}_far_thresh"] = np.float32(far_thresh)
         out[f"probe_{tag}_keep"] = ns["neighboring_miss_mask"].numpy()
         assert 0 < out[f"probe_{tag}_keep"].sum() < H * W
+    # ---- the probe outputs (models/neural_points_volumetric_model.py:334-355): the body of `if weight is not None:` executed on
+    # seeded tensors of the shapes run_network_models hands it (B = 1)
+    lines = open(os.path.join(REF, "models/neural_points_volumetric_model.py")).read().split("\n")
+    first = next(i for i, ln in enumerate(lines) if 'output["ray_max_shading_opacity"], opacity_ind = torch.max(' in ln)
+    last = next(i for i, ln in enumerate(lines) if 'output["shading_avg_embedding"] = torch.sum(sampled_embedding * weight' in ln)
+    print("probe output lines (1-based):", first + 1, "-", last + 1)
+    body = textwrap.dedent("\n".join(lines[first:last + 1]))
+    g = torch.Generator().manual_seed(11)
+    R, SR, K = 37, 12, 8
+    rnd = lambda *sh: torch.rand(sh, generator=g)
+    ns = {"torch": torch, "output": {"coarse_point_opacity": rnd(1, R, SR)}, "sample_loc_w": rnd(1, R, SR, 3) * 2 - 1,
+          "weight": rnd(1, R, SR, K), "conf_coefficient": rnd(1, R, SR, K), "sampled_xyz": rnd(1, R, SR, K, 3) * 2 - 1,
+          "sampled_color": rnd(1, R, SR, K, 3), "sampled_dir": rnd(1, R, SR, K, 3) * 2 - 1, "sampled_conf": rnd(1, R, SR, K, 1),
+          "sampled_embedding": rnd(1, R, SR, K, 32)}
+    ns["output"]["coarse_point_opacity"][0, 5, 3] = ns["output"]["coarse_point_opacity"][0, 5, 7] = 2.0      # a tie: torch.max keeps the first
+    inputs = {k: v.clone() for k, v in ns.items() if torch.is_tensor(v)}
+    inputs["coarse_point_opacity"] = ns["output"]["coarse_point_opacity"].clone()
+    exec(body, ns)
+    for k, v in inputs.items():
+        out[f"probeout_in_{k}"] = v.numpy()
+    for k in ("ray_max_shading_opacity", "ray_max_sample_loc_w", "ray_max_far_dist", "shading_avg_color", "shading_avg_dir",
+              "shading_avg_conf", "shading_avg_embedding"):
+        out[f"probeout_{k}"] = ns["output"][k].numpy()
     np.savez_compressed(os.path.join(HERE, "cloud_ops_golden.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -35,3 +35,19 @@ def test_vox_closest_matches_the_reference_function():
         np.testing.assert_array_equal(grid, G[f"vox_{tag}_grid"])
         np.testing.assert_allclose(cen, G[f"vox_{tag}_centroid"], rtol=0, atol=2e-7)
         assert_same_argmin(xyz, cen, amin, G[f"vox_{tag}_min_idx"])
+
+
+def test_probe_outputs_match_the_reference_lines():
+    """oracle.field.probe (the checker of pnerf_probe, tests/test_gpu_parity.py::test_probe_prune_grow) against the outputs of the
+    reference's own lines (models/neural_points_volumetric_model.py:334-355) executed on the same tensors."""
+    import torch
+    from oracle import field as of
+    t = lambda k: torch.from_numpy(G[f"probeout_in_{k}"])[0]
+    g = {"mask": torch.ones(t("weight").shape, dtype=torch.bool), "loc_w": t("sample_loc_w"), "xyz": t("sampled_xyz"),
+         "color": t("sampled_color"), "dir": t("sampled_dir"), "conf": t("sampled_conf"), "embed": t("sampled_embedding")}
+    extras = {"weight_used": t("weight"), "conf_coefficient": t("conf_coefficient")}
+    got = of.probe(None, g, extras, t("coarse_point_opacity"))
+    for k in ("ray_max_shading_opacity", "ray_max_sample_loc_w", "ray_max_far_dist", "shading_avg_color", "shading_avg_dir",
+              "shading_avg_conf", "shading_avg_embedding"):
+        want = G[f"probeout_{k}"][0]
+        np.testing.assert_allclose(got[k].numpy().reshape(want.shape), want, rtol=1e-6, atol=1e-7, err_msg=k)
