@@ -862,6 +862,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_ker
                 }
 #pragma unroll
                 for (int q = 24; q < 32; q++) t[q] = 0.f;
+                t[24] = 1.f;      // column 280: multiplied by a zero weight here; the backward's weight-gradient GEMM reads it as the ones column of d bc1
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const uint4 pv = pack8(t + 8 * q);

@@ -10,10 +10,10 @@
 //   wgrad_tc_kernel  (TC)    dW_L = delta_L^T X_{L-1}: both operands are the saved tiles read as MN-major operands (the k-slab
 //                            layout IS the canonical no-swizzle MN-major layout with LBO and SBO swapped), K = the 128 rows of a
 //                            tile, accumulated over a CTA's tiles in TMEM (128 x 288 fp32), fp32 red.add into dW at the end
-//   colsum_kernel    (SIMT)  d b_L = column sums of delta_L
+//                            the bias gradients d b_L = delta_L^T 1 ride in the same GEMM (a constant-1 input column)
 //   scatter_kernel   (SIMT)  d embed (raw + through the positional encoding), d color, d dir, d conf -> atomics by point id
 // The colour network (mlp_color + rgb head) takes the same route on 128-sample tiles kept by color_tc_kernel<SAVE>: color_head_bwd_kernel
-// (SIMT) -> tile_gemm_kernel x3 (K = 128) -> the same wgrad / colsum launches (job tables).
+// (SIMT) -> tile_gemm_kernel x3 (K = 128) -> the same wgrad launch (job table).
 #include "pnerf_common.cuh"
 #include "tc_layout.cuh"
 #include "umma.cuh"
@@ -247,6 +247,7 @@ struct WgJob {
     const uint8_t* x; int64_t x_stride; int x_slab0, xslabs;  // the layer's input tiles
     float* dW; int in_dim, out0;                              // (out, in_dim) fp32, accumulated into; first output feature of the job
     int n_tiles, spt;                                         // tile capacity, samples per tile
+    float* db; int bias_col;                                  // bias gradient (out) and the accumulator column that holds it, see below
 };
 constexpr int WG_MAX_JOBS = 12;
 struct WgradP { WgJob j[WG_MAX_JOBS]; int n_jobs; const int* S_dev; };
@@ -257,6 +258,11 @@ struct WgSmem {
     uint32_t tmem_base;
 };
 
+// Bias gradients ride in the same GEMM: db_L = column sums of delta_L = delta_L^T . 1, i.e. the column of dW_L that belongs to a constant-1
+// input.  The layer-1 / layer-3 / colour-layer-1 input tiles already carry that column (284 / 263 / 280: the bias column of the forward
+// GEMMs, resp. a padding column the forward sets to 1 against a zero weight); for the 256- and 128-wide inputs a persistent ones slab sits
+// behind the tile in shared memory and a 16-column tail MMA accumulates it.  (Round 1 ran a separate colsum_kernel over all seven
+// gradient tiles: 0.135 of a 1.55 ms training step.)
 __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw);
@@ -266,16 +272,27 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
     const int n_tiles = dyn_tiles(p.S_dev, jb.n_tiles, jb.spt);
     const int n_my = n_tiles > part ? (n_tiles - part + parts - 1) / parts : 0;
     const int xslabs = jb.xslabs;
+    const bool ones_tail = xslabs <= 32;                       // the input tile has no constant-1 column of its own
     if (tid == 0) {
         for (int s = 0; s < 2; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
         mbar_init(&sm.done, 1);
         fence_barrier_init();
+    }
+    if (ones_tail) {       // slabs xslabs, xslabs + 1 of both stages: column 0 = 1 for all 128 rows, the other 15 columns 0 (never overwritten: a CTA serves one job)
+        for (int i = tid; i < 2 * 2 * ROWS; i += 256) {
+            const int s = i / (2 * ROWS), r = i % (2 * ROWS);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (r < ROWS) v.x = 0x00003F80u;                   // bf16 1.0 in element 0 of the row's 16 bytes
+            reinterpret_cast<uint4*>(sm.X[s] + (size_t)xslabs * SLAB)[r] = v;
+        }
+        fence_proxy_async();
     }
     if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    const int tail_slab0 = ones_tail ? xslabs : 32, tail_n = ones_tail ? 16 : 32;
     if (warp == 0) {
         if (lane == 0) {            // producer
             for (int i = 0; i < n_my; i++) {
@@ -290,7 +307,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
     } else if (warp == 1) {
         if (lane == 0 && n_my > 0) {   // MMA issuer: both operands MN-major (k = tile rows): LBO = 128 (next 8 rows), SBO = SLAB (next 8 features)
             const uint32_t mn = (1u << 15) | (1u << 16);
-            const uint32_t idesc_main = make_idesc_bf16(ROWS, xslabs >= 32 ? 256 : xslabs * 8) | mn, idesc_tail = make_idesc_bf16(ROWS, 32) | mn;
+            const uint32_t idesc_main = make_idesc_bf16(ROWS, xslabs >= 32 ? 256 : xslabs * 8) | mn, idesc_tail = make_idesc_bf16(ROWS, tail_n) | mn;
             for (int i = 0; i < n_my; i++) {
                 const int s = i & 1;
                 mbar_wait(&sm.full[s], (uint32_t)((i >> 1) & 1));
@@ -300,10 +317,8 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
                     const uint64_t ad = make_smem_desc(d_base + (uint32_t)(ks * 256), 128, SLAB);
                     const uint64_t bd = make_smem_desc(x_base + (uint32_t)(ks * 256), 128, SLAB);
                     mma_bf16(tmem, ad, bd, idesc_main, (uint32_t)((i | ks) > 0));
-                    if (xslabs > 32) {
-                        const uint64_t bt = make_smem_desc(x_base + (uint32_t)(32 * SLAB + ks * 256), 128, SLAB);
-                        mma_bf16(tmem + 256u, ad, bt, idesc_tail, (uint32_t)((i | ks) > 0));
-                    }
+                    const uint64_t bt = make_smem_desc(x_base + (uint32_t)(tail_slab0 * SLAB + ks * 256), 128, SLAB);
+                    mma_bf16(tmem + (uint32_t)(tail_slab0 * 8), ad, bt, idesc_tail, (uint32_t)((i | ks) > 0));
                 }
                 mma_commit(&sm.empty[s]);
             }
@@ -315,52 +330,23 @@ __global__ void __launch_bounds__(256, 1) wgrad_tc_kernel(const WgradP p) {
         const int o = jb.out0 + (warp & 3) * 32 + lane;          // output feature = accumulator lane
         const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         float* dst = jb.dW + (int64_t)o * jb.in_dim;
-        const int in_dim = jb.in_dim;
+        const int in_dim = jb.in_dim, bias_col = jb.bias_col;
+        const int n_cols = tail_slab0 * 8 + tail_n;
 #pragma unroll 1
-        for (int c0 = 0; c0 < xslabs * 8; c0 += 32) {
+        for (int c0 = 0; c0 < n_cols; c0 += 32) {
             float v[32];
             tmem_ld32(tacc + (uint32_t)c0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j++)
-                if (c0 + j < in_dim) atomicAdd(dst + c0 + j, v[j]);
+            for (int j = 0; j < 32; j++) {
+                if (c0 + j < in_dim) { if (jb.dW) atomicAdd(dst + c0 + j, v[j]); }
+                else if (c0 + j == bias_col && jb.db) atomicAdd(jb.db + o, v[j]);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-// ---------------------------------------------------------------------------------------------- bias gradients
-// db_L[c] = sum over rows of delta_L[r][c].  Thread = (slab, 16-row group); block = one tile at a time.
-struct ColsumJob { const uint8_t* d; int64_t d_stride; int n_slabs; float* db; int n_tiles, spt; };
-struct ColsumP { ColsumJob j[7]; const int* S_dev; };
-__global__ void __launch_bounds__(256) colsum_kernel(const ColsumP p) {
-    __shared__ float s_part[8][HID];
-    const ColsumJob jb = p.j[blockIdx.y];
-    const int t = threadIdx.x;
-    const int slab = t >> 3, rg = t & 7;
-    float acc[8] = {};
-    if (slab < jb.n_slabs) {
-        const int n_tiles = dyn_tiles(p.S_dev, jb.n_tiles, jb.spt);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const uint4* src = reinterpret_cast<const uint4*>(jb.d + (int64_t)tile * jb.d_stride + (int64_t)slab * SLAB) + rg * 16;
-#pragma unroll 4
-            for (int r = 0; r < 16; r++) {
-                float f[8];
-                unpack8(__ldg(src + r), f);
-#pragma unroll
-                for (int e = 0; e < 8; e++) acc[e] += f[e];
-            }
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; e++) s_part[rg][slab * 8 + e] = acc[e];
-    __syncthreads();
-    float sum = 0.f;
-#pragma unroll
-    for (int g = 0; g < 8; g++) sum += s_part[g][t];
-    if (jb.db && t < jb.n_slabs * 8) atomicAdd(jb.db + t, sum);
 }
 
 // ---------------------------------------------------------------------------------------------- rgb head backward
@@ -642,14 +628,18 @@ extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_came
         g.S_dev = S_dev;
         int nj = 0;
         float* dWf[4] = {gm->w1, gm->w2, gm->w3, gm->w4};
+        float* dbf[4] = {gm->b1, gm->b2, gm->b3, gm->b4};
         const int in_dim[4] = {284, 256, 263, 256}, xoff[4] = {SAVE_X0, SAVE_H1, SAVE_X3, SAVE_H3}, xsl[4] = {36, 32, 36, 32};
+        const int bcol[4] = {284, 256, 263, 256};              // the constant-1 column of the layer's input (X0 / X3: in the tile; H1 / H3: the ones slab)
         for (int L = 0; L < 4; L++)
             for (int h = 0; h < 2; h++)
-                if (dWf[L]) g.j[nj++] = {w.d[L], DELTA_TILE_BYTES, 16 * h, w.save, SAVE_TILE_BYTES, xoff[L], xsl[L], dWf[L], in_dim[L], 128 * h, n_tiles, ROWS / KP};
+                if (dWf[L] || dbf[L]) g.j[nj++] = {w.d[L], DELTA_TILE_BYTES, 16 * h, w.save, SAVE_TILE_BYTES, xoff[L], xsl[L], dWf[L], in_dim[L], 128 * h, n_tiles, ROWS / KP,
+                                         dbf[L], bcol[L]};
         float* dWc[3] = {gm->wc1, gm->wc2, gm->wc3};
-        const int cin[3] = {280, 128, 128}, coff[3] = {CSAVE_C0, CSAVE_C1, CSAVE_C2}, csl[3] = {36, 16, 16};
+        float* dbc[3] = {gm->bc1, gm->bc2, gm->bc3};
+        const int cin[3] = {280, 128, 128}, coff[3] = {CSAVE_C0, CSAVE_C1, CSAVE_C2}, csl[3] = {36, 16, 16}, cbcol[3] = {280, 128, 128};
         for (int L = 0; L < 3; L++)
-            if (dWc[L]) g.j[nj++] = {w.dc[L], CDELTA_TILE_BYTES, 0, w.csave, CSAVE_TILE_BYTES, coff[L], csl[L], dWc[L], cin[L], 0, n_ctiles, ROWS};
+            if (dWc[L] || dbc[L]) g.j[nj++] = {w.dc[L], CDELTA_TILE_BYTES, 0, w.csave, CSAVE_TILE_BYTES, coff[L], csl[L], dWc[L], cin[L], 0, n_ctiles, ROWS, dbc[L], cbcol[L]};
         g.n_jobs = nj;
         if (nj > 0) {
             const size_t wsm = sizeof(WgSmem);
@@ -657,13 +647,6 @@ extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_came
             wgrad_tc_kernel<<<nj * (kSMs / nj), 256, wsm, st>>>(g);
             PNERF_LAUNCH_CHECK();
         }
-        ColsumP c;
-        c.S_dev = S_dev;
-        float* db[7] = {gm->b1, gm->b2, gm->b3, gm->b4, gm->bc1, gm->bc2, gm->bc3};
-        for (int i = 0; i < 4; i++) c.j[i] = {w.d[i], DELTA_TILE_BYTES, 32, db[i], n_tiles, ROWS / KP};
-        for (int i = 0; i < 3; i++) c.j[4 + i] = {w.dc[i], CDELTA_TILE_BYTES, 16, db[4 + i], n_ctiles, ROWS};
-        colsum_kernel<<<dim3(n_tiles < 64 ? n_tiles : 64, 7), 256, 0, st>>>(c);
-        PNERF_LAUNCH_CHECK();
     }
     return PNERF_OK;
 }
