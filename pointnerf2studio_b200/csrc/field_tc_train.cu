@@ -420,77 +420,75 @@ struct ScatterP {
     int S, SR, K, KP, n_tiles, weight_conf; const int* S_dev;
     float *g_embed, *g_color, *g_dir, *g_conf;
 };
-__global__ void __launch_bounds__(128) scatter_kernel(const ScatterP p) {
-    __shared__ float s_w3e[HID][8];
-    for (int i = threadIdx.x; i < HID * 8; i += 128) { const int c = i >> 3, j = i & 7; s_w3e[c][j] = j < 7 ? p.w3[(int64_t)c * 263 + 256 + j] : 0.f; }
-    __syncthreads();
-    const int row = threadIdx.x;
+// One WARP per neighbour row (round 1: one thread per row, whose 896 B of dx0 and 512 B of delta_3 were read uncoalesced and whose
+// 1792-FMA extras product ran serially: 0.19 ms per 136 k rows, 38 long-scoreboard stalls per issue).  Lane d owns embedding dimension d
+// (its 7 dx0 values, one coalesced 128-byte red.add per row) and the 8 delta_3 columns of k-slab d (the 56 weights of the extras
+// product stay in its registers); the 7 extras gradients are warp-reduced.
+__global__ void __launch_bounds__(256) scatter_kernel(const ScatterP p) {
+    const int lane = threadIdx.x & 31;
     const int spt = ROWS / p.KP;
     const int S = dyn_count(p.S_dev, p.S), n_tiles = dyn_tiles(p.S_dev, p.n_tiles, spt);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    float w3r[8][7];                         // mlp_head.layers.0 weight, columns 256..262 (the 7 extras), rows 8 * lane .. 8 * lane + 7
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+#pragma unroll
+        for (int x = 0; x < 7; x++) w3r[e][x] = __ldg(p.w3 + (int64_t)(8 * lane + e) * 263 + 256 + x);
+    const int64_t n_rows = (int64_t)n_tiles * ROWS;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t grow = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grow < n_rows; grow += warps) {
+        const int tile = (int)(grow / ROWS), row = (int)(grow % ROWS);
         const int si = tile * spt + row / p.KP, k = row % p.KP;
-        if (si >= S || k >= p.K) continue;
-        const int slot = p.sample_ids[si];
-        const int pt = p.sample_pidx[(int64_t)slot * p.K + k];
+        if (si >= S || k >= p.K) continue;                      // warp-uniform
+        const int slot = __ldg(p.sample_ids + si);
+        const int pt = __ldg(p.sample_pidx + (int64_t)slot * p.K + k);
         if (pt < 0) continue;
-        const int64_t grow = (int64_t)tile * ROWS + row;
         if (p.g_embed) {
             const float* dx = p.dx0 + grow * NX0;
-            const float4* e4 = reinterpret_cast<const float4*>(p.embed + (int64_t)pt * 32);
-            float4* g4 = reinterpret_cast<float4*>(p.g_embed + (int64_t)pt * 32);
-#pragma unroll 2
-            for (int q = 0; q < 8; q++) {
-                const float4 ev = __ldg(e4 + q);
-                const float e[4] = {ev.x, ev.y, ev.z, ev.w};
-                float g[4];
+            float acc = __ldg(dx + lane);
+            const float e = __ldg(p.embed + (int64_t)pt * 32 + lane);
+            float sn, cs;
+            __sincosf(e, &sn, &cs);                           // as the forward encoder: one sincos + double-angle recurrences
+            const float2 q0 = __ldg(reinterpret_cast<const float2*>(dx + 32 + 6 * lane));
+            const float2 q1 = __ldg(reinterpret_cast<const float2*>(dx + 32 + 6 * lane + 2));
+            const float2 q2 = __ldg(reinterpret_cast<const float2*>(dx + 32 + 6 * lane + 4));
+            const float ds[3] = {q0.x, q1.x, q2.x}, dc[3] = {q0.y, q1.y, q2.y};
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int d = 4 * q + i;
-                    float acc = dx[d];
-                    float sn, cs;
-                    __sincosf(e[i], &sn, &cs);             // as the forward encoder: one sincos + double-angle recurrences
-#pragma unroll
-                    for (int f = 0; f < 3; f++) {          // d sin(2^f x) = 2^f cos, d cos(2^f x) = -2^f sin (SU:61-67 layout)
-                        const float sc = (float)(1 << f);
-                        acc = fmaf(dx[32 + (d * 3 + f) * 2], sc * cs, acc);
-                        acc = fmaf(dx[32 + (d * 3 + f) * 2 + 1], -sc * sn, acc);
-                        const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
-                        sn = s2; cs = c2;
-                    }
-                    g[i] = acc;
-                }
-                atomicAdd(g4 + q, make_float4(g[0], g[1], g[2], g[3]));
+            for (int f = 0; f < 3; f++) {                      // d sin(2^f x) = 2^f cos, d cos(2^f x) = -2^f sin (SU:61-67 layout)
+                const float sc = (float)(1 << f);
+                acc = fmaf(ds[f], sc * cs, acc);
+                acc = fmaf(dc[f], -sc * sn, acc);
+                const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn;
+                sn = s2; cs = c2;
             }
+            atomicAdd(p.g_embed + (int64_t)pt * 32 + lane, acc);
         }
         if (p.g_color || p.g_dir) {
-            float de[7] = {};
-            const uint4* drow = reinterpret_cast<const uint4*>(p.d3 + (int64_t)tile * DELTA_TILE_BYTES + row * 16);
-#pragma unroll 2
-            for (int j = 0; j < HID / 8; j++) {
-                float f[8];
-                unpack8(__ldg(drow + j * (SLAB / 16)), f);
+            float f[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.d3 + (int64_t)tile * DELTA_TILE_BYTES + row * 16) + lane * (SLAB / 16)), f);
+            float de[7];
 #pragma unroll
-                for (int e = 0; e < 8; e++)
+            for (int x = 0; x < 7; x++) {
+                float a = 0.f;
 #pragma unroll
-                    for (int x = 0; x < 7; x++) de[x] = fmaf(f[e], s_w3e[8 * j + e][x], de[x]);
+                for (int e = 0; e < 8; e++) a = fmaf(f[e], w3r[e][x], a);
+#pragma unroll
+                for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                de[x] = a;
             }
-            if (p.g_color) { atomicAdd(p.g_color + 3 * (int64_t)pt, de[0]); atomicAdd(p.g_color + 3 * (int64_t)pt + 1, de[1]); atomicAdd(p.g_color + 3 * (int64_t)pt + 2, de[2]); }
-            if (p.g_dir) {
+            if (p.g_color && lane < 3) atomicAdd(p.g_color + 3 * (int64_t)pt + lane, lane == 0 ? de[0] : (lane == 1 ? de[1] : de[2]));
+            if (p.g_dir && lane < 3) {
                 // dr = dir . Rn ; e[3+j] = dr_j - v_j ; e[6] = <dr, v>  ->  d dr_j = de[3+j] + de[6] v_j ; d dir_i = sum_j d dr_j Rw2c[j][i]
                 const int ray = slot / p.SR;
                 const float rd[3] = {p.dirs[3 * ray], p.dirs[3 * ray + 1], p.dirs[3 * ray + 2]};
                 float v[3];
                 rot_w2c(p.cam, rd, v);
+                float gi = 0.f;
 #pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    float gi = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 3; j++) gi = fmaf(de[3 + j] + de[6] * v[j], p.cam.Rw[3 * j + i], gi);
-                    atomicAdd(p.g_dir + 3 * (int64_t)pt + i, gi);
-                }
+                for (int j = 0; j < 3; j++) gi = fmaf(de[3 + j] + de[6] * v[j], p.cam.Rw[3 * j + lane], gi);
+                atomicAdd(p.g_dir + 3 * (int64_t)pt + lane, gi);
             }
         }
-        if (p.g_conf && p.weight_conf) {   // w = wn * clamp(conf): d conf = d w * wn (straight-through clamp, PA:740-742)
+        if (p.g_conf && p.weight_conf && lane == 0) {   // w = wn * clamp(conf): d conf = d w * wn (straight-through clamp, PA:740-742)
             const float cc = fminf(fmaxf(p.conf[pt], 1e-4f), 1.f);
             atomicAdd(p.g_conf + pt, p.dw_rows[grow] * (p.save_w[grow] / cc));
         }
@@ -618,7 +616,7 @@ extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_came
         s.dx0 = w.dx0; s.d3 = w.d[2]; s.w3 = mlp->w3; s.dw_rows = w.dw_rows; s.save_w = w.save_w;
         s.S = S; s.S_dev = S_dev; s.SR = SR; s.K = K; s.KP = KP; s.n_tiles = n_tiles; s.weight_conf = mode->weight_conf;
         s.g_embed = g_embed; s.g_color = g_color; s.g_dir = g_dir; s.g_conf = g_conf;
-        scatter_kernel<<<n_tiles < kSMs * 8 ? n_tiles : kSMs * 8, 128, 0, st>>>(s);
+        scatter_kernel<<<n_tiles * 16 < kSMs * 8 ? n_tiles * 16 : kSMs * 8, 256, 0, st>>>(s);
         PNERF_LAUNCH_CHECK();
     }
     if (points_done_event) PNERF_CUDA(cudaEventRecord((cudaEvent_t)points_done_event, st));

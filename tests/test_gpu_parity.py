@@ -496,3 +496,30 @@ def test_fused_adam_updates_reach_the_bf16_forward():
         assert float((seq[3] - seq[1]).abs().max()) > 1e-3, precision
     for a, b in zip(outs["fp32"], outs["bf16"]):
         assert float((a - b).abs().max()) <= 3e-2
+
+
+def test_neural_points_forward_returns_the_reference_tuple():
+    """NeuralPoints.forward (SU:147-209): the 13 gathered tensors the reference's get_outputs consumes, for a caller that keeps the
+    reference's own field math (INTEGRATION.md level 2) -- same order, shapes and values as the oracle's gather."""
+    s, cloud, cam, pix = _scene("config1")
+    frame, raypos, t_mid, pidx_o, loc_o, mask_o, hit_o, _ = _oracle_query(cloud.xyz, cam, pix, s["SR"], s["K"], s["P"], s["ks"])
+    cp, cl, cm = gq.compact_rays(pidx_o, loc_o, hit_o)
+    pts = {"xyz": torch.from_numpy(cloud.xyz)}
+    for k in ("embed", "color", "dir", "conf"):
+        pts[k] = torch.from_numpy(getattr(cloud, k))
+    rays = torch.from_numpy(cam.rays(pix))
+    g = of.gather(torch.from_numpy(cp), pts, torch.from_numpy(cl), rays[torch.from_numpy(cm).bool()], torch.from_numpy(cam.R_c2w),
+                  torch.from_numpy(cam.origin), s["SR"])
+    model = _make_model(cloud, "fp32", "plugin", SR=s["SR"], K=s["K"], P=s["P"])
+    out = model.neural_points(_bundle(cam, pix))
+    assert len(out) == 13
+    (col, Rw2c, dr, emb, xyz_pers, xyz, conf, loc_pers, loc_w, mask, ray_dirs, vsize, ray_mask) = out
+    B, R2, SR, K = mask.shape
+    assert (B, R2, SR, K) == (1,) + cp.shape and ray_mask.shape == (1, len(pix)) and ray_mask.dtype == torch.int8
+    np.testing.assert_array_equal(ray_mask[0].cpu().numpy(), cm)
+    np.testing.assert_array_equal(mask[0].cpu().numpy(), g["mask"].numpy())
+    np.testing.assert_array_equal(loc_w[0].cpu().numpy(), cl)
+    for got, want, tol in ((col, g["color"], 0), (dr, g["dir"], 0), (emb, g["embed"], 0), (xyz, g["xyz"], 0), (conf, g["conf"], 0),
+                           (xyz_pers, g["xyz_pers"], 1e-5), (loc_pers, g["loc_pers"], 1e-5), (ray_dirs, g["ray_dirs"], 0)):
+        np.testing.assert_allclose(got[0].cpu().numpy(), want.numpy(), rtol=tol, atol=tol * 10)
+    assert torch.equal(Rw2c.cpu(), torch.from_numpy(cloud.Rw2c)) and list(vsize) == [0.004] * 3
