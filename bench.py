@@ -15,6 +15,7 @@ The default line (`--workload render`, BASELINE configs[1]) carries, besides the
   parity  (N = 1)                 : the CPU oracle on a pixel sample of the SAME view with the very t table the GPU's in-kernel
                                     jitter generated (pnerf_coarse_t): neighbour-index mismatches, pixel error, PSNR.  The same
                                     CPU run is the `cpu_baseline`.
+  stress  (configs[4], N = 1)     : ~10 M-point cloud, K = 16, SR = 80, 5^3 kernel: query GB/s and aggregation TFLOP/s on 65 536 rays.
   scannet (configs[3], N > 1 or --with-scannet) : ONE 1296x968 image of a 3 M-point cloud split over the ranks by interleaved
                                     rows (strong scaling); device-timed with the pixel all-gather, end to end with every rank
                                     copying its rows straight into one shared pinned host image.
@@ -510,6 +511,48 @@ def bench_scannet(c, steps, warmup, n_points=3_000_000):
                         "all-gather; 3M-point synthetic cloud, K=8, SR=24, voxel 0.016, P=30 (configs[3])"}
 
 
+def bench_stress(c, reps=3, n_points=10_000_000, n_rays=65536):
+    """configs[4]: Tanks-and-Temples-scale stress -- ~10 M-point cloud, K = 16, SR = 80, vsize 0.002 x vscale 2, kernel 5^3 (3 layers,
+    125 voxels), P = 10 (dev_scripts/w_tt_ft/truck_points.sh:53-63): the neighbour query and the aggregation (fused field kernels)
+    timed separately on `n_rays` rays of a 1024x1024 view.  The cloud is generated on the GPU (synth.make_cloud_state_dict_torch)."""
+    from pointnerf2studio_b200 import PointNerf, PointNerfConfig, RayBundle, native
+    from pointnerf2studio_b200.synth import make_camera, make_cloud_state_dict_torch
+    sd, stats = make_cloud_state_dict_torch(n_points, seed=1239, device="cuda", scaled_vsize=0.004, P=10, radii=(0.45, 0.65, 0.85), kernel_size=(5, 5, 5))
+    cfg = PointNerfConfig(K=16, SR=80, P=10, vsize=[0.002] * 3, kernel_size=[5, 5, 5], max_o=1600000, precision=c.precision)
+    model = PointNerf(cfg, state_dict=sd).eval()
+    own = dict(model.named_parameters())
+    with torch.no_grad():
+        for k, v in c.weights.items():
+            own[k].copy_(v)
+    cam = make_camera(H=1024, W=1024, focal=1422.0)
+    pix = np.sort(np.random.default_rng(n_rays).choice(cam.H * cam.W, size=n_rays, replace=False))
+    rb = RayBundle.for_camera(torch.from_numpy(cam.rays(pix)).cuda(), cam.origin, cam.R_c2w, cam.near, cam.far)
+    with torch.no_grad():
+        model.get_outputs(rb)                         # builds the grid, warms up
+        st = query_stats(model, rb)
+        native.Timers.enabled, native.Timers.spans = True, []
+        for _ in range(reps):
+            c.flush.add_(1.0)
+            model.get_outputs(rb)
+        torch.cuda.synchronize()
+        sp = {k: sum(v) / len(v) for k, v in native.Timers.collect().items()}
+        native.Timers.enabled = False
+    q_bytes = 12.0 * st["filled"] + 4.0 * st["vis"] + 16.0 * st["cand"] + 4.0 * cfg.K * st["filled"]
+    flops = FIELD_FLOP_ROW * st["M"] + COLOR_FLOP_SAMPLE * st["S"]
+    out = {"workload": "Tanks-and-Temples-scale stress: ~10M-point cloud, K=16, SR=80, 5x5x5 kernel, voxel 0.004, P=10 (configs[4])",
+           "rays": n_rays, "n_points": stats["n_points"], "cloud": stats, "filled_slots": st["filled"], "valid_samples_S": st["S"],
+           "neighbour_rows_M": st["M"], "mean_voxels_visited": st["vis"] / max(st["filled"], 1), "mean_candidates": st["cand"] / max(st["filled"], 1),
+           "ms": sp, "query_samples_per_s": st["filled"] / (sp["query"] * 1e-3),
+           "query_hbm": {"achieved": q_bytes / (sp["query"] * 1e-3) / 1e9, "peak": c.peaks["hbm"], "unit": "GB/s",
+                         "frac": q_bytes / (sp["query"] * 1e-3) / 1e9 / c.peaks["hbm"]},
+           "aggregate_rows_per_s": st["M"] / (sp["field"] * 1e-3),
+           "aggregate_tensor": {"achieved": flops / (sp["field"] * 1e-3) / 1e12, "peak": c.peaks["tensor"], "unit": "TFLOP/s",
+                                "frac": flops / (sp["field"] * 1e-3) / 1e12 / c.peaks["tensor"]}}
+    del model, sd
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -526,6 +569,7 @@ def main():
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--with-scannet", action="store_true", help="add the configs[3] block at N = 1 too (always on at N > 1)")
     ap.add_argument("--no-scannet", action="store_true")
+    ap.add_argument("--no-stress", action="store_true", help="skip the configs[4] block (10M points, K=16; on by default at N = 1)")
     ap.add_argument("--no-graph", action="store_true", help="train block: launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="gradient exchange of the train block at N > 1")
     args = ap.parse_args()
@@ -662,6 +706,11 @@ def main():
                                           "fed the GPU kernel's jittered t table so that its pixels double as the parity check"}
     if not args.no_train:
         line["train"] = bench_train(c, cam, train_steps, args.warmup)
+    if world == 1 and not args.no_stress and args.points == N_POINTS:
+        del model
+        c.model = None
+        torch.cuda.empty_cache()
+        line["stress"] = bench_stress(c)
     if (world > 1 or args.with_scannet) and not args.no_scannet:
         del model
         c.model = None

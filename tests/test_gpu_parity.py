@@ -521,5 +521,5 @@ def test_neural_points_forward_returns_the_reference_tuple():
     np.testing.assert_array_equal(loc_w[0].cpu().numpy(), cl)
     for got, want, tol in ((col, g["color"], 0), (dr, g["dir"], 0), (emb, g["embed"], 0), (xyz, g["xyz"], 0), (conf, g["conf"], 0),
                            (xyz_pers, g["xyz_pers"], 1e-5), (loc_pers, g["loc_pers"], 1e-5), (ray_dirs, g["ray_dirs"], 0)):
-        np.testing.assert_allclose(got[0].cpu().numpy(), want.numpy(), rtol=tol, atol=tol * 10)
+        np.testing.assert_allclose(got[0].detach().cpu().numpy(), want.numpy(), rtol=tol, atol=tol * 10)
     assert torch.equal(Rw2c.cpu(), torch.from_numpy(cloud.Rw2c)) and list(vsize) == [0.004] * 3
