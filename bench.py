@@ -15,7 +15,7 @@ The default line (`--workload render`, BASELINE configs[1]) carries, besides the
   parity  (N = 1)                 : the CPU oracle on a pixel sample of the SAME view with the very t table the GPU's in-kernel
                                     jitter generated (pnerf_coarse_t): neighbour-index mismatches, pixel error, PSNR.  The same
                                     CPU run is the `cpu_baseline`.
-  stress  (configs[4], N = 1)     : ~10 M-point cloud, K = 16, SR = 80, 5^3 kernel: query GB/s and aggregation TFLOP/s on 65 536 rays.
+  stress  (configs[4], N = 1)     : ~10 M-point cloud, K = 16, SR = 80, 5^3 kernel: query GB/s and aggregation TFLOP/s on 262 144 rays.
   scannet (configs[3], N > 1 or --with-scannet) : ONE 1296x968 image of a 3 M-point cloud split over the ranks by interleaved
                                     rows (strong scaling); device-timed with the pixel all-gather, end to end with every rank
                                     copying its rows straight into one shared pinned host image.
@@ -511,7 +511,7 @@ def bench_scannet(c, steps, warmup, n_points=3_000_000):
                         "all-gather; 3M-point synthetic cloud, K=8, SR=24, voxel 0.016, P=30 (configs[3])"}
 
 
-def bench_stress(c, reps=3, n_points=10_000_000, n_rays=65536):
+def bench_stress(c, reps=3, n_points=10_000_000, n_rays=262144):
     """configs[4]: Tanks-and-Temples-scale stress -- ~10 M-point cloud, K = 16, SR = 80, vsize 0.002 x vscale 2, kernel 5^3 (3 layers,
     125 voxels), P = 10 (dev_scripts/w_tt_ft/truck_points.sh:53-63): the neighbour query and the aggregation (fused field kernels)
     timed separately on `n_rays` rays of a 1024x1024 view.  The cloud is generated on the GPU (synth.make_cloud_state_dict_torch)."""
