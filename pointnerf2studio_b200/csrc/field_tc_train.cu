@@ -157,7 +157,10 @@ struct GemmSmem {
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(256, 1) tile_gemm_kernel(const GemmP p) {
+// 12 warps: warp 0 producer + MMA issuer, warps 4-7 / 8-11 the epilogue of the lower / upper column half (a warp reaches the TMEM
+// lanes of its quarter warp % 4 only, so two warps share a quarter and split the columns: the epilogue -- 32 mask loads, 256
+// multiplies, 32 stores per row -- was the longest stage of a tile with one warp per quarter).
+__global__ void __launch_bounds__(384, 1) tile_gemm_kernel(const GemmP p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     GemmSmem& sm = *reinterpret_cast<GemmSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(256, 1) tile_gemm_kernel(const GemmP p) {
     const int n_my = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (tid == 0) {
         mbar_init(&sm.w_bar, 1); mbar_init(&sm.a_full, 1); mbar_init(&sm.a_free, 1);
-        for (int b = 0; b < 2; b++) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 4); }
+        for (int b = 0; b < 2; b++) { mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 8); }
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(&sm.tmem_base, 512);
@@ -201,6 +204,8 @@ __global__ void __launch_bounds__(256, 1) tile_gemm_kernel(const GemmP p) {
         }
     } else if (warp >= 4) {
         const int row = (warp & 3) * 32 + lane;
+        const int split = N > 128 ? 128 : 64;                    // N = 256 / 224 / 128: 128 + 128, 128 + 96, 64 + 64 columns
+        const int cbeg = warp >= 8 ? split : 0, cend = warp >= 8 ? N : split;
         for (int i = 0; i < n_my; i++) {
             const int tile = (int)blockIdx.x + i * (int)gridDim.x, b = i & 1;
             mbar_wait(&sm.acc_full[b], (uint32_t)((i >> 1) & 1));
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(256, 1) tile_gemm_kernel(const GemmP p) {
             uint4* orow = p.out_bf ? reinterpret_cast<uint4*>(p.out_bf + (int64_t)tile * p.out_stride + row * 16) : nullptr;
             float* frow = p.out_f32 ? p.out_f32 + ((int64_t)tile * ROWS + row) * p.ld_f32 : nullptr;
 #pragma unroll 1
-            for (int c0 = 0; c0 < N; c0 += 32) {
+            for (int c0 = cbeg; c0 < cend; c0 += 32) {
                 float v[32];
                 tmem_ld32(tacc + (uint32_t)c0, v);
                 tmem_ld_wait();
@@ -575,7 +580,7 @@ extern "C" int pnerf_field_backward_tc(const pnerf_points* pts, const pnerf_came
         g.in = in; g.in_stride = in_stride; g.ks = ks; g.mask = mask; g.mask_stride = mask_stride;
         g.out_bf = out_bf; g.out_stride = out_stride; g.out_f32 = out_f32; g.ld_f32 = ld;
         g.w = w.wbwd + wb; g.N = N; g.n_tiles = tiles; g.slope = slope;
-        tile_gemm_kernel<<<tiles < kSMs ? tiles : kSMs, 256, gsm, st>>>(g);
+        tile_gemm_kernel<<<tiles < kSMs ? tiles : kSMs, 384, gsm, st>>>(g);
         PNERF_LAUNCH_CHECK();
         return PNERF_OK;
     };

@@ -4,10 +4,13 @@ Same names, argument meaning and outputs as
   pointnerf/nerfstudio/studio_model.py  (PointNerfConfig SM:61-118, PointNerf SM:122-504)
   pointnerf/nerfstudio/studio_utils.py  (NeuralPoints SU:71-209, PointNeRFEncoding SU:47-68)
 but `get_outputs` runs on libpnerf_b200.so: grid built once per cloud version, sample selection +
-neighbour query + field networks + compositing as CUDA kernels, no per-call host syncs on the
-bf16 path.  Nerfstudio is not required: `PointNerf` is a plain nn.Module that accepts any object with
-`origins (R,3)`, `directions (R,3)`, `nears/fars (R,1)`, `metadata["camrotc2w"]`; the registration
-shim for `ns-train pointnerf-original` lives in nerfstudio_plugin.py.
+neighbour query + field networks + compositing as CUDA kernels.  Host syncs per call: NONE on the bf16
+training path (one custom op, the data-dependent counts stay on the device); the inference paths read
+back the sizes of their data-dependent launches (R' after the hit-ray compaction of an image, the
+per-class sample counts) and -- for a bundle without the `camera_host` hint -- ray 0's camera once.
+Nerfstudio is not required: without it `PointNerf` is a plain nn.Module that accepts any object with
+`origins (R,3)`, `directions (R,3)`, `nears/fars (R,1)`, `metadata["camrotc2w"]`; with it, it is a
+nerfstudio `Model`.  The `ns-train pointnerf-original` registration lives in nerfstudio_plugin.py.
 """
 from __future__ import annotations
 
