@@ -457,58 +457,13 @@ def render_f32(cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, mlp_params):
     return _RenderF32.apply(cfg, q, dirs, xyz, Rw2c, embed, color, dirn, conf, *mlp_params)
 
 
-class _MaskedMSE(torch.autograd.Function):
-    """get_loss_dict's MSELoss over the masked rays + 1e-6 (studio_model.py:415-426) as one kernel each way."""
-
-    @staticmethod
-    def forward(ctx, pred, image, ray_mask):
-        lib = _lib.load()
-        pred_c, image_c = pred.detach().contiguous(), image.detach().contiguous()
-        acc = torch.zeros((4,), dtype=torch.float32, device=pred.device)        # [sum sq, #masked, ticket, loss]
-        check(lib.pnerf_masked_mse_forward(_ptr(pred_c, torch.float32), _ptr(image_c, torch.float32), _ptr(ray_mask, torch.int8),
-                                           pred_c.shape[0], _ptr(acc), C.c_void_p(acc.data_ptr() + 12), _stream()),
-              "pnerf_masked_mse_forward")
-        LAUNCHES["n"] += 1
-        ctx.save_for_backward(pred_c, image_c, ray_mask, acc)
-        return acc[3]
-
-    @staticmethod
-    def backward(ctx, d):
-        lib = _lib.load()
-        pred, image, ray_mask, acc = ctx.saved_tensors
-        g = torch.empty_like(pred)
-        d = d.detach().to(torch.float32).contiguous()
-        check(lib.pnerf_masked_mse_backward(_ptr(pred), _ptr(image), _ptr(ray_mask), pred.shape[0], _ptr(acc), _ptr(d), _ptr(g), _stream()),
-              "pnerf_masked_mse_backward")
-        LAUNCHES["n"] += 1
-        return g, None, None
-
-
 def masked_mse(pred: torch.Tensor, image: torch.Tensor, ray_mask: torch.Tensor):
-    return _MaskedMSE.apply(pred, image, ray_mask)
+    """get_loss_dict's MSELoss over the masked rays + 1e-6 (studio_model.py:415-426): the `pnerf::masked_mse` custom op (ops.py)."""
+    from . import ops  # noqa: F401  (registers the op)
+    return torch.ops.pnerf.masked_mse(pred, image.contiguous(), ray_mask)[0]
 
 
-def conf_loss(conf: torch.Tensor, q_pidx: torch.Tensor, ray_mask: torch.Tensor, n_rays: torch.Tensor, eps: float,
-              weight: float):
-    """Zero-one confidence loss of studio_model.py:288-292,427-429 with its analytic gradient."""
-    return _ConfLoss.apply(conf, q_pidx, ray_mask, n_rays, eps, weight)
-
-
-class _ConfLoss(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, conf, pidx, ray_mask, n_rays, eps, weight):
-        lib = _lib.load()
-        R, SR, K = pidx.shape
-        loss = torch.zeros((1,), dtype=torch.float32, device=conf.device)
-        g = torch.zeros_like(conf)
-        check(lib.pnerf_conf_loss(_ptr(conf.detach().contiguous()), _ptr(pidx), _ptr(ray_mask), R, SR, K, C.c_float(eps),
-                                  C.c_float(weight), _ptr(n_rays), _ptr(loss), _ptr(g), C.c_float(1.0), _stream()),
-              "pnerf_conf_loss")
-        LAUNCHES["n"] += 1
-        ctx.save_for_backward(g)
-        return loss[0]
-
-    @staticmethod
-    def backward(ctx, d):
-        (g,) = ctx.saved_tensors
-        return g * d, None, None, None, None, None
+def conf_loss(conf: torch.Tensor, q_pidx: torch.Tensor, ray_mask: torch.Tensor, n_rays: torch.Tensor, eps: float, weight: float):
+    """Zero-one confidence loss of studio_model.py:288-292,427-429 with its analytic gradient: the `pnerf::conf_loss` custom op."""
+    from . import ops  # noqa: F401
+    return torch.ops.pnerf.conf_loss(conf, q_pidx, ray_mask, n_rays, float(eps), float(weight))[0]
