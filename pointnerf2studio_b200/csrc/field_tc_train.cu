@@ -429,15 +429,19 @@ struct ScatterP {
 // 1792-FMA extras product ran serially: 0.19 ms per 136 k rows, 38 long-scoreboard stalls per issue).  Lane d owns embedding dimension d
 // (its 7 dx0 values, one coalesced 128-byte red.add per row) and the 8 delta_3 columns of k-slab d (the 56 weights of the extras
 // product stay in its registers); the 7 extras gradients are warp-reduced.
-__global__ void __launch_bounds__(256) scatter_kernel(const ScatterP p) {
+// The kernel is latency-bound (a chain of four dependent global loads per row: sample id -> point id -> embedding / gradients): what
+// counts is warps in flight, so the 56 extras weights of a lane live in shared memory ([x][e][lane]: conflict-free) instead of
+// registers (100 -> ~48 registers, 2 -> 5 blocks per SM).
+__global__ void __launch_bounds__(256, 5) scatter_kernel(const ScatterP p) {
+    __shared__ float s_w3[7 * 8 * 32];       // mlp_head.layers.0 weight, columns 256..262 (the 7 extras): [x][e][lane] = W3[8 * lane + e][256 + x]
     const int lane = threadIdx.x & 31;
     const int spt = ROWS / p.KP;
     const int S = dyn_count(p.S_dev, p.S), n_tiles = dyn_tiles(p.S_dev, p.n_tiles, spt);
-    float w3r[8][7];                         // mlp_head.layers.0 weight, columns 256..262 (the 7 extras), rows 8 * lane .. 8 * lane + 7
-#pragma unroll
-    for (int e = 0; e < 8; e++)
-#pragma unroll
-        for (int x = 0; x < 7; x++) w3r[e][x] = __ldg(p.w3 + (int64_t)(8 * lane + e) * 263 + 256 + x);
+    for (int i = threadIdx.x; i < 7 * 8 * 32; i += 256) {
+        const int x = i / 256, e = (i / 32) % 8, l = i % 32;
+        s_w3[i] = __ldg(p.w3 + (int64_t)(8 * l + e) * 263 + 256 + x);
+    }
+    __syncthreads();
     const int64_t n_rows = (int64_t)n_tiles * ROWS;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t grow = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grow < n_rows; grow += warps) {
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const ScatterP p) {
             for (int x = 0; x < 7; x++) {
                 float a = 0.f;
 #pragma unroll
-                for (int e = 0; e < 8; e++) a = fmaf(f[e], w3r[e][x], a);
+                for (int e = 0; e < 8; e++) a = fmaf(f[e], s_w3[(x * 8 + e) * 32 + lane], a);
 #pragma unroll
                 for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
                 de[x] = a;
