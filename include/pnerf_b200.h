@@ -106,10 +106,13 @@ int pnerf_coarse_t(float near_t, float far_t, float jitter, uint64_t seed, int R
  * (d2, visit order) and are emitted in that order; d2 = fma(dz,dz,fma(dy,dy,dx*dx)).
  * outputs: sample_pidx (R,SR,K) with -1 padding (every slot is written);
  *          sample_valid (R*SR) uint8: the number of neighbours found for the slot (0 = none; every consumer tests it for != 0);
- *          stats (optional, 2 x uint64): voxel-table entries visited, candidate points examined. */
+ *          stats (optional, 2 x uint64): voxel-table entries visited, candidate points examined;
+ *          rays_are_neighbours: a scheduling hint with no effect on the result -- non-zero when consecutive rays are neighbouring
+ *          pixels of one image (the hit-ray list of a render): a warp then takes the same slot of 32 consecutive rays instead of
+ *          32 consecutive slots of one ray (candidate streams of similar length, better balanced lock-step). */
 int pnerf_query(const pnerf_grid_view* grid_h, const float* sample_loc, const int* sample_cnt, int R, int SR,
                 int K, int kernel_size0, float radius, int* sample_pidx, uint8_t* sample_valid,
-                unsigned long long* stats, void* stream);
+                unsigned long long* stats, int rays_are_neighbours, void* stream);
 
 /* Ray compaction of the reference's return value (CU:425-432): ray_mask (R) int8 and, when the
  * caller wants the reference's compact (R'',SR,.) tensors, an index list of the surviving rays.

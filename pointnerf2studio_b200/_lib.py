@@ -93,7 +93,7 @@ SIGNATURES = {
     "pnerf_coarse_t": (C.c_int, [C.c_float, C.c_float, C.c_float, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
     "pnerf_query": (C.c_int, [C.POINTER(GridView), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
-                              C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                              C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pnerf_ray_compact": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_void_p]),
     "pnerf_gather_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -40,7 +40,7 @@ extern "C" int pnerf_render_train_forward(const pnerf_grid_view* grid, const pne
         else
             rc = pnerf_sample_select_jitter(grid, cam->origin, dirs, near_t, far_t, jitter, seed, R, D, SR, 1, b->sample_loc, b->sample_cnt, stream);
         if (rc) return rc;
-        if ((rc = pnerf_query(grid, b->sample_loc, b->sample_cnt, R, SR, K, kernel_size0, radius, b->sample_pidx, b->sample_valid, nullptr, stream))) return rc;
+        if ((rc = pnerf_query(grid, b->sample_loc, b->sample_cnt, R, SR, K, kernel_size0, radius, b->sample_pidx, b->sample_valid, nullptr, 0, stream))) return rc;
         if ((rc = pnerf_sample_compact(b->sample_valid, slots, b->sample_ids, b->n_samples, scan_ws, scan_bytes, stream))) return rc;
     }
     if (!(phases & 2)) return PNERF_OK;

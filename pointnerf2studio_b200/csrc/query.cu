@@ -245,27 +245,34 @@ __global__ void __launch_bounds__(128, KMAX <= 8 ? PNERF_Q_MINB : (KMAX == 16 ? 
                                                      const float4* __restrict__ recs, const float* __restrict__ sample_loc,
                                                      const int* __restrict__ sample_cnt, int R, int SR, int K, int layers,
                                                      float r2, int max_runs, int* __restrict__ sample_pidx,
-                                                     uint8_t* __restrict__ sample_valid, unsigned long long* __restrict__ stats) {
+                                                     uint8_t* __restrict__ sample_valid, unsigned long long* __restrict__ stats,
+                                                     int across_rays) {
     extern __shared__ int s_runs[];                    // [max_runs][2][128]: start / length of run j of thread t at (j*2 + {0,1})*128 + t
     const int lane = threadIdx.x & 31, t = threadIdx.x;
+    // Which 32 samples share a warp.  along a ray (across_rays = 0): 32 consecutive slots of one ray -- right for a batch of unrelated
+    // rays (training: random pixels).  across rays (1): the SAME slot of 32 consecutive rays -- right for the hit-ray list of an image,
+    // whose neighbours are neighbouring pixels: their s-th samples sit at nearly the same depth, so the 32 candidate streams are of
+    // similar length (the lock-step trip count is the warp's longest stream: 58 against a mean of 34 along a ray, where a warp spans
+    // the whole passage through the surface shell) and lie closer together (32 pixels ~ 14 voxels against 40 along the ray).
     const int cpr = (SR + 31) >> 5;                    // 32-slot chunks per ray
-    const int64_t n_tasks = (int64_t)R * cpr;
+    const int64_t n_tasks = across_rays ? (int64_t)((R + 31) >> 5) * SR : (int64_t)R * cpr;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long n_vis = 0, n_cand = 0;
     for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_tasks; w += warps) {
-        const int r = (int)(w / cpr);
-        const int slot = (int)(w % cpr) * 32 + lane;
+        const int r = across_rays ? (int)(w / SR) * 32 + lane : (int)(w / cpr);
+        const int slot = across_rays ? (int)(w % SR) : (int)(w % cpr) * 32 + lane;
+        const bool in_range = r < R && slot < SR;
         const int64_t sid = (int64_t)r * SR + slot;
         float bd2[KMAX];
         int bidx[KMAX];
 #pragma unroll
         for (int i = 0; i < KMAX; i++) { bd2[i] = INFINITY; bidx[i] = -1; }
-        const int cnt = __ldg(sample_cnt + r);
-        if ((int)(w % cpr) * 32 < cnt) {               // warp-uniform: some slot of this chunk is filled
+        const int cnt = r < R ? __ldg(sample_cnt + r) : 0;
+        if (__any_sync(0xffffffffu, in_range && slot < cnt)) {      // some sample of this warp is filled
             float qx = 0.f, qy = 0.f, qz = 0.f;
             int vx = 0, vy = 0, vz = 0;
             bool searching = false;
-            if (slot < cnt && slot < SR) {
+            if (in_range && slot < cnt) {
                 qx = __ldg(sample_loc + 3 * sid); qy = __ldg(sample_loc + 3 * sid + 1); qz = __ldg(sample_loc + 3 * sid + 2);
                 searching = voxel_of(f, qx, qy, qz, vx, vy, vz);
             }
@@ -329,7 +336,7 @@ __global__ void __launch_bounds__(128, KMAX <= 8 ? PNERF_Q_MINB : (KMAX == 16 ? 
                 if (!__any_sync(0xffffffffu, searching)) break;
             }
         }
-        if (slot < SR) {
+        if (in_range) {
             int* out = sample_pidx + sid * K;
             if (K == KMAX && (KMAX % 4) == 0) {
 #pragma unroll
@@ -429,7 +436,7 @@ extern "C" int pnerf_coarse_t(float near, float far, float jitter, uint64_t seed
 
 extern "C" int pnerf_query(const pnerf_grid_view* g, const float* sample_loc, const int* sample_cnt, int R, int SR, int K,
                            int kernel_size0, float radius, int* sample_pidx, uint8_t* sample_valid,
-                           unsigned long long* stats, void* stream) {
+                           unsigned long long* stats, int rays_are_neighbours, void* stream) {
     if (!g || R < 0 || SR <= 0 || K <= 0 || K > 32) return PNERF_ERR_ARG;
     const int layers = (kernel_size0 + 1) / 2;   // CU:256 reads kernel_size[0] only
     if (layers < 1 || layers > 3) return PNERF_ERR_ARG;
@@ -437,14 +444,14 @@ extern "C" int pnerf_query(const pnerf_grid_view* g, const float* sample_loc, co
     if (!sample_loc || !sample_cnt || !sample_pidx || !sample_valid || !g->cell_start || !g->recs) return PNERF_ERR_ARG;
     const Frame f = frame_of(g);
     const float r2 = radius * radius;            // CU:410, fp32 on the host
-    const int64_t tasks = (int64_t)R * ((SR + 31) / 32);
+    const int64_t tasks = rays_are_neighbours ? (int64_t)((R + 31) / 32) * SR : (int64_t)R * ((SR + 31) / 32);
     const int blocks = (int)min((int64_t)kSMs * 16, (tasks * 32 + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* recs = (const float4*)g->recs;
     const int max_runs = layers == 1 ? 1 : (layers == 2 ? 10 : 34);     // runs of the largest shell: 1, 8 + 2, 16 + 18
     const size_t smem = (size_t)max_runs * 2 * 128 * sizeof(int);
 #define PNERF_LAUNCH_Q(KM) \
-    query_kernel<KM><<<blocks, 128, smem, st>>>(f, g->cell_start, recs, sample_loc, sample_cnt, R, SR, K, layers, r2, max_runs, sample_pidx, sample_valid, stats)
+    query_kernel<KM><<<blocks, 128, smem, st>>>(f, g->cell_start, recs, sample_loc, sample_cnt, R, SR, K, layers, r2, max_runs, sample_pidx, sample_valid, stats, rays_are_neighbours ? 1 : 0)
     if (K <= 4) PNERF_LAUNCH_Q(4);
     else if (K <= 8) PNERF_LAUNCH_Q(8);
     else if (K <= 16) PNERF_LAUNCH_Q(16);

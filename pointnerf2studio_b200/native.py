@@ -158,7 +158,7 @@ def coarse_t(near: float, far: float, jitter: float, seed: int, R: int, D: int, 
 def sample_and_query(grid: VoxelGrid, R: int, D: int, SR: int, K: int, kernel_size0: int, radius: float,
                      raypos: Optional[torch.Tensor] = None, origin=None, dirs: Optional[torch.Tensor] = None,
                      t_vals: Optional[torch.Tensor] = None, want_stats: bool = False, jitter_gen=None,
-                     compact: bool = False) -> QueryResult:
+                     compact: bool = False, across_rays: Optional[bool] = None) -> QueryResult:
     """Rows G0/G2/Q: select the first SR occupied coarse positions per ray and query K neighbours each.
     Position source: `raypos` (R,D,3), or origin + dirs * `t_vals` ((D,) or (R,D)), or -- `jitter_gen` =
     (near, far, jitter, seed) -- jittered t generated inside the selection kernel.
@@ -204,8 +204,10 @@ def sample_and_query(grid: VoxelGrid, R: int, D: int, SR: int, K: int, kernel_si
     pidx = torch.empty((R, SR, K), dtype=torch.int32, device=dev)
     valid = torch.empty((R, SR), dtype=torch.uint8, device=dev)
     with Timers.span("query"):
+        # the compacted hit-ray list of an image keeps neighbouring pixels next to each other: warps take one slot of 32 rays
+        hint = compact if across_rays is None else bool(across_rays)
         check(lib.pnerf_query(C.byref(grid.view), _ptr(loc), _ptr(cnt), R, SR, K, int(kernel_size0), C.c_float(float(radius)),
-                              _ptr(pidx), _ptr(valid), _ptr(stats), _stream()), "pnerf_query")
+                              _ptr(pidx), _ptr(valid), _ptr(stats), 1 if hint else 0, _stream()), "pnerf_query")
     LAUNCHES["n"] += 2
     return QueryResult(loc, cnt, pidx, valid, stats, ray_index, R_total, dirs_c)
 

@@ -359,7 +359,7 @@ def sample_query(dirs: Tensor, cell_start: Tensor, recs: Tensor, occ_bits: Tenso
     else:
         check(lib.pnerf_sample_select(C.byref(gv), None, origin, _p(dirs), _p(t_vals), it[IT_TSTRIDE], R, D, SR, 1, _p(loc), _p(cnt), st),
               "pnerf_sample_select")
-    check(lib.pnerf_query(C.byref(gv), _p(loc), _p(cnt), R, SR, K, it[IT_KS0], C.c_float(fl[FL_RADIUS]), _p(pidx), _p(valid), None, st),
+    check(lib.pnerf_query(C.byref(gv), _p(loc), _p(cnt), R, SR, K, it[IT_KS0], C.c_float(fl[FL_RADIUS]), _p(pidx), _p(valid), None, 0, st),
           "pnerf_query")
     native.LAUNCHES["n"] += 2
     return loc, cnt, pidx, valid

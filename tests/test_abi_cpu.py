@@ -116,11 +116,11 @@ def test_argument_errors_are_return_codes_not_crashes():
     lib = _lib.load()
     ERR_ARG, OK = -1, 0
     assert lib.pnerf_bbox(None, 10, None, None) == ERR_ARG
-    assert lib.pnerf_query(None, None, None, 4, 8, 8, 3, C.c_float(0.016), None, None, None, None) == ERR_ARG
+    assert lib.pnerf_query(None, None, None, 4, 8, 8, 3, C.c_float(0.016), None, None, None, 0, None) == ERR_ARG
     g = _lib.GridView()
-    assert lib.pnerf_query(C.byref(g), None, None, 4, 8, 40, 3, C.c_float(0.016), None, None, None, None) == ERR_ARG      # K > 32
-    assert lib.pnerf_query(C.byref(g), None, None, 4, 8, 8, 9, C.c_float(0.016), None, None, None, None) == ERR_ARG       # 9^3 kernel
-    assert lib.pnerf_query(C.byref(g), None, None, 0, 8, 8, 3, C.c_float(0.016), None, None, None, None) == OK            # no rays
+    assert lib.pnerf_query(C.byref(g), None, None, 4, 8, 40, 3, C.c_float(0.016), None, None, None, 0, None) == ERR_ARG      # K > 32
+    assert lib.pnerf_query(C.byref(g), None, None, 4, 8, 8, 9, C.c_float(0.016), None, None, None, 0, None) == ERR_ARG       # 9^3 kernel
+    assert lib.pnerf_query(C.byref(g), None, None, 0, 8, 8, 3, C.c_float(0.016), None, None, None, 0, None) == OK            # no rays
     assert lib.pnerf_sample_select(C.byref(g), None, None, None, None, 0, 4, 400, 8, 1, None, None, None) == ERR_ARG
     assert lib.pnerf_sample_select_jitter(C.byref(g), None, None, C.c_float(6.0), C.c_float(2.0), C.c_float(0.3), 1, 4, 400, 8, 1,
                                           None, None, None) == ERR_ARG                                                     # far <= near

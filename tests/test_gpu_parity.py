@@ -123,6 +123,10 @@ def test_grid_select_query_bit_exact(name):
         np.testing.assert_array_equal(q.sample_valid.cpu().numpy().astype(bool), (pidx_o >= 0).any(-1))
         st = q.stats.cpu().numpy()
         assert st[0] == stats_o[..., 0][mask_o].sum() and st[1] == stats_o[..., 1][mask_o].sum()
+    # the warp mapping is a scheduling choice: one slot of 32 consecutive rays per warp gives the same bits as 32 slots of one ray
+    q2 = native.sample_and_query(grid, R, 400, s["SR"], s["K"], s["ks"][0], float(np.float32(4 * vs)), raypos=_cuda(raypos.numpy()),
+                                 want_stats=True, across_rays=True)
+    assert torch.equal(q2.sample_pidx, q.sample_pidx) and torch.equal(q2.sample_valid, q.sample_valid) and torch.equal(q2.stats, q.stats)
     assert (pidx_o >= 0).sum() > 1000
 
 
