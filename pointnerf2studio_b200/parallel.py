@@ -217,13 +217,31 @@ class TrainEngine:
         self.exchange = exchange
         self._hdl_p = self._hdl_g = None
         if exchange == "p2p":
-            import torch.distributed._symmetric_memory as symm_mem
-            group = dist.group.WORLD.group_name
-            self.P = symm_mem.empty(padded, dtype=torch.float32, device=dev)
-            self.G = symm_mem.empty(padded, dtype=torch.float32, device=dev)
-            self._hdl_p, self._hdl_g = symm_mem.rendezvous(self.P, group), symm_mem.rendezvous(self.G, group)
-            self.P.zero_()
-        else:
+            # symmetric memory is a collective set-up: every rank reports how far it got and all fall back to NCCL together
+            def agree(ok: bool) -> bool:
+                flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                return bool(flag.item())
+            why = None
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                group = dist.group.WORLD.group_name
+                self.P = symm_mem.empty(padded, dtype=torch.float32, device=dev)
+                self.G = symm_mem.empty(padded, dtype=torch.float32, device=dev)
+            except Exception as e:      # noqa: BLE001
+                why = e
+            if agree(why is None):
+                try:
+                    self._hdl_p, self._hdl_g = symm_mem.rendezvous(self.P, group), symm_mem.rendezvous(self.G, group)
+                    self.P.zero_()
+                except Exception as e:  # noqa: BLE001
+                    why = e
+            if not agree(why is None):
+                import warnings
+                warnings.warn(f"TrainEngine: peer-mapped buffers unavailable ({why!r}); falling back to the NCCL all-reduce route")
+                exchange = self.exchange = "nccl"
+                self._hdl_p = self._hdl_g = None
+        if exchange != "p2p":
             self.P = torch.zeros(padded, dtype=torch.float32, device=dev)
             self.G = torch.empty(padded, dtype=torch.float32, device=dev)
         self.G.zero_()

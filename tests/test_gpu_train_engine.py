@@ -163,3 +163,35 @@ def test_graph_replay_tracks_the_eager_engine_over_changing_cameras():
         d = (pa[n] - pb[n]).abs()
         assert float(d.mean()) <= 3e-4 and float((d > 2e-3).float().mean()) <= 0.02, (n, float(d.mean()), float(d.max()))
     assert float((ia - ib).abs().max()) <= 2e-2
+
+
+def test_custom_ops_pass_opcheck():
+    """torch.library.opcheck on the registered ops: the schema matches what the implementations do (nothing mutated, no aliasing) and
+    the fake (meta) implementations produce the shapes / dtypes / devices of the real ones -- i.e. the boundary is traceable."""
+    from pointnerf2studio_b200 import native, native_tc, ops
+    s, cloud, cam, pix = _scene("config1")
+    pix = pix[:256]
+    m = _make_model(cloud, "bf16", "plugin", SR=24, K=s["K"], P=s["P"]).train()
+    npnts, c = m.neural_points, m.config
+    rb = _bundle(cam, pix)
+    origin, R_c2w, near, far = npnts.camera_of(rb, with_near_far=True)
+    grid = npnts.grid()
+    mode = native.make_mode("plugin", training=True, bg=[1.0, 1.0, 1.0], vsize_z=0.004)
+    t = npnts.coarse_t(len(pix), near, far, 0.0)
+    fl, it = ops.fl_it(grid.frame, origin, R_c2w, native._rw2c_host(npnts.points_Rw2c), near, far, 0.0, float(npnts.radius_limit_np), mode,
+                       c.z_depth_dim, c.SR, c.K, 3)
+    params = [p.detach() for p in m.mlp_param_list()]
+    wpack = native_tc.packed_weights(m.mlp_param_list())[0]
+    dirs = rb.directions.contiguous()
+    args = (dirs, npnts.points_xyz.detach(), npnts.points_embeding.detach().view(-1, 32), npnts.points_color.detach().view(-1, 3),
+            npnts.points_dir.detach().view(-1, 3), npnts.points_conf.detach().view(-1, 1), params, wpack, grid.cell_start, grid.recs,
+            grid.occ_bits, t, None, None, None, fl, it)
+    checks = ("test_schema", "test_faketensor")
+    torch.library.opcheck(torch.ops.pnerf.render_train.default, args, test_utils=checks)
+    torch.library.opcheck(torch.ops.pnerf.sample_query.default, (dirs, grid.cell_start, grid.recs, grid.occ_bits, t, fl, it), test_utils=checks)
+    out = torch.ops.pnerf.render_train(*args)
+    pred, ray_mask, n_rays, pidx = out[0], out[1], out[2], out[3]
+    img = torch.rand_like(pred)
+    torch.library.opcheck(torch.ops.pnerf.masked_mse.default, (pred, img, ray_mask), test_utils=checks + ("test_autograd_registration",))
+    torch.library.opcheck(torch.ops.pnerf.conf_loss.default, (npnts.points_conf.detach().view(-1, 1), pidx, ray_mask, n_rays, 1e-3, 1e-4),
+                          test_utils=checks + ("test_autograd_registration",))
