@@ -93,7 +93,7 @@ def test_train_engine_tracks_the_per_group_optimisers():
         for k in opts:
             opts[k].step()
             scheds[k].step()
-        assert abs(float(la) - float(lb)) <= 2e-3 * max(abs(float(la)), 1e-3), (it, float(la), float(lb))
+        assert abs(float(la.detach()) - float(lb.detach())) <= 2e-3 * max(abs(float(la.detach())), 1e-3), (it, float(la.detach()), float(lb.detach()))
     assert float(eng.G.abs().max()) == 0.0                        # gradients are reset for the next step
     pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
     for n in names:
