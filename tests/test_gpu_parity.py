@@ -527,3 +527,22 @@ def test_neural_points_forward_returns_the_reference_tuple():
                            (xyz_pers, g["xyz_pers"], 1e-5), (loc_pers, g["loc_pers"], 1e-5), (ray_dirs, g["ray_dirs"], 0)):
         np.testing.assert_allclose(got[0].detach().cpu().numpy(), want.numpy(), rtol=tol, atol=tol * 10)
     assert torch.equal(Rw2c.cpu(), torch.from_numpy(cloud.Rw2c)) and list(vsize) == [0.004] * 3
+
+
+def test_shared_host_image_receives_interleaved_rows():
+    """parallel.SharedHostImage: every rank copies the interleaved rows it rendered into ONE pinned host image with a strided copy.
+    Single process standing in for world = 3: three instances on the same mapping, one per rank."""
+    from pointnerf2studio_b200.parallel import SharedHostImage, interleaved_rows
+    H, W, world = 37, 53, 3
+    full = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(4)).cuda()
+    imgs = [SharedHostImage(H, W, r, world, None, tag=f"pnerf_test_{os.getpid()}") if r == 0 else None for r in range(world)]
+    for r in range(1, world):          # the other "ranks" map the file rank 0 created
+        imgs[r] = SharedHostImage.__new__(SharedHostImage)
+        imgs[r].__dict__.update(imgs[0].__dict__)
+        imgs[r].rank = r
+    for r in range(world):
+        rows = interleaved_rows(H, r, world)
+        imgs[r].put_rows(full[rows].reshape(-1, 3).contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(imgs[0].image, full.cpu())
+    imgs[0].close()
