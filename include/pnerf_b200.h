@@ -216,7 +216,7 @@ int64_t pnerf_tc_wpack_bytes(void);
 int pnerf_tc_pack_weights(const pnerf_mlp* mlp_h, void* wpack, void* stream);
 int64_t pnerf_field_tc_workspace_bytes(int64_t n_samples);
 /* The two kernels of pnerf_field_forward_tc on their own, for sample lists bucketed by neighbour count
- * (pnerf_sample_compact_classes): the per-neighbour networks of `n_samples` samples with `rows_per_sample` (1, 2, 4, 8, 16 or 32,
+ * (pnerf_sample_compact_classes): the per-neighbour networks of `n_samples` samples with `rows_per_sample` (2, 4, 8, 16 or 32,
  * >= every listed sample's neighbour count) MMA rows each, writing the aggregated features of sample i to position
  * first_sample + i of `workspace` (512 B per sample, 128-sample tiles); then ONE colour-network launch over the whole list. */
 int pnerf_field_forward_tc_part(const pnerf_points* pts_h, const pnerf_camera* cam_h, const pnerf_mlp* mlp_h, const void* wpack,

@@ -72,7 +72,7 @@ constexpr int ENC_PARTS = PNERF_ENC_PARTS;       // threads per row in the encod
 constexpr int EPW = PNERF_EPW;                           // epilogue warps per slot: 4 (a warp drains all 256 columns of its 32 lanes) or 8 (128 each)
 constexpr int ENCW = 4 * ENC_PARTS;
 constexpr int NT = (ENCW + 2 * EPW + 2) * 32;    // encoder + 2 x EPW epilogue + producer + issuer warps
-constexpr int MAX_SPT = 128;                     // samples per tile at KP = 1
+constexpr int MAX_SPT = 64;                      // samples per tile at KP = 2
 
 // colour network
 constexpr int HC = 128;
@@ -1080,7 +1080,6 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     else if (save) rc = KP == 8 ? launch(field_tc_kernel<8, true>) : (KP == 16 ? launch(field_tc_kernel<16, true>) : (KP == 32 ? launch(field_tc_kernel<32, true>) : PNERF_ERR_ARG));
     else {
         switch (KP) {
-            case 1: rc = launch(field_tc_kernel<1, false>); break;
             case 2: rc = launch(field_tc_kernel<2, false>); break;
             case 4: rc = launch(field_tc_kernel<4, false>); break;
             case 8: rc = launch(field_tc_kernel<8, false>); break;
@@ -1136,7 +1135,7 @@ extern "C" int pnerf_field_forward_tc_part(const pnerf_points* pts, const pnerf_
                                            void* workspace, int64_t workspace_bytes, void* stream) {
     if (!pts || !cam || !mlp || !wpack || !mode || S < 0 || K <= 0 || K > 32 || SR <= 0 || first_sample < 0) return PNERF_ERR_ARG;
     const int kp = rows_per_sample;
-    if (kp != 1 && kp != 2 && kp != 4 && kp != 8 && kp != 16 && kp != 32) return PNERF_ERR_ARG;
+    if (kp != 2 && kp != 4 && kp != 8 && kp != 16 && kp != 32) return PNERF_ERR_ARG;
     if (S == 0) return PNERF_OK;
     if (!workspace || workspace_bytes < pnerf_field_tc_workspace_bytes((int64_t)first_sample + S)) return PNERF_ERR_WORKSPACE;
     if (!(mode->lrelu_slope > 0.f && mode->lrelu_slope < 1.f)) return PNERF_ERR_ARG;

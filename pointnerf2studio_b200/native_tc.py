@@ -42,12 +42,12 @@ def packed_weights(mlp_params, force: bool = False):
 
 
 def class_rows(K: int):
-    """Rows-per-sample classes for lists bucketed by neighbour count: the power of two >= K, then its halves down to 1."""
-    kp = 1
+    """Rows-per-sample classes for lists bucketed by neighbour count: the power of two >= K, then its halves down to 2."""
+    kp = 2
     while kp < K:
         kp *= 2
     out = [kp]
-    while out[-1] > 1:
+    while out[-1] > 2:
         out.append(out[-1] // 2)
     return out
 

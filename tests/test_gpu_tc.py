@@ -160,7 +160,7 @@ def test_sample_lists_bucketed_by_neighbour_count():
             for s_ in range(SR):
                 pidx[r, s_, :cnt[r, s_]] = rng.integers(0, 1000, size=cnt[r, s_])
         ids, counts, kps = native_tc.compact_sample_classes(torch.from_numpy(cnt.astype(np.uint8)).cuda(), K)
-        assert kps == native_tc.class_rows(K) and kps[0] >= K and kps[-1] == 1
+        assert kps == native_tc.class_rows(K) and kps[0] >= K and kps[-1] == 2
         ids = ids.cpu().numpy()
         flat = cnt.reshape(-1)
         off = 0

@@ -8,8 +8,8 @@ import torch
 
 def test_class_rows():
     from pointnerf2studio_b200.native_tc import class_rows
-    assert class_rows(8) == [8, 4, 2, 1] and class_rows(16) == [16, 8, 4, 2, 1] and class_rows(3) == [4, 2, 1] and class_rows(1) == [1]
-    assert class_rows(32) == [32, 16, 8, 4, 2, 1]
+    assert class_rows(8) == [8, 4, 2] and class_rows(16) == [16, 8, 4, 2] and class_rows(3) == [4, 2] and class_rows(1) == [2]
+    assert class_rows(32) == [32, 16, 8, 4, 2]
 
 
 def test_adam_step_scalars_follow_torch_and_the_schedule():
