@@ -9,7 +9,8 @@ The default line (`--workload render`, BASELINE configs[1]) carries, besides the
                                     scaled voxel 0.008 through the whole hot path (coarse positions, sample selection,
                                     neighbour query, field networks, compositing).  N GPUs: every rank renders a DIFFERENT
                                     view (azimuth 30 + 45 * rank degrees; ray-sharded by view, cloud replicated) and the
-                                    pixels of all views are all-gathered inside the timed region -> weak scaling.
+                                    pixels of all views are all-gathered inside the device-timed region -> weak scaling; end to
+                                    end every rank uploads its rays and downloads its own view (no collective on that route).
   train   (configs[2])            : fwd + bwd + gradient all-reduce (N > 1) + Adam on 4096 rays per rank, the reference's own
                                     per-process batch (studio_config.py:20-21); `update_ms` (exchange + Adam) is reported separately.
   parity  (N = 1)                 : the CPU oracle on a pixel sample of the SAME view with the very t table the GPU's in-kernel
@@ -335,9 +336,10 @@ def bench_render(c, cam, steps, warmup):
 
     def step_e2e():
         # one camera per call: the directions are the per-ray input; origin / rotation / near / far are 14 floats
+        # (every rank serves its own view from and to ITS host buffers: no collective on this route -- the all-gather above is for a
+        # device-side consumer of all the frames and belongs to the device-timed figure)
         rb = RayBundle.for_camera(host[1].cuda(non_blocking=True), cam.origin, cam.R_c2w, cam.near, cam.far)
         o = model.get_outputs_for_camera_ray_bundle(rb)
-        gather(o["coarse_raycolor"])
         out_host.copy_(o["coarse_raycolor"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
