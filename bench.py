@@ -410,6 +410,17 @@ def bench_train(c, cam, steps, warmup):
     for _ in range(2):
         step_e2e()
     ms_e2e = timed_steps(step_e2e, steps, c.flush, dist)
+    # for information: the same 4096 rays split over the ranks = strong scaling of ONE batch
+    strong = None
+    if dist is not None and TRAIN_RAYS % world == 0:
+        r_s = TRAIN_RAYS // world
+        rb_s = to_device(host_bundle(cam, pix[:r_s]), RayBundle)
+        gt_s = gt_dev[:r_s].contiguous()
+        for _ in range(3):
+            engine.step(rb_s, gt_s)
+        ms_s = max_over_ranks([timed_steps(lambda: engine.step(rb_s, gt_s), steps, c.flush, dist)], dist)[0]
+        strong = {"rays_per_step_total": TRAIN_RAYS, "rays_per_step_per_gpu": r_s, "ms_per_step": ms_s / steps,
+                  "value": TRAIN_RAYS * steps / (ms_s * 1e-3), "unit": "rays/s", "scaling": "strong"}
     if engine._graphs:       # per-stage device times need eager launches: a few untimed steps outside the graph (diagnostic only)
         engine.use_graph = False
         for _ in range(2):
@@ -453,6 +464,7 @@ def bench_train(c, cam, steps, warmup):
             "e2e": {"value": rays_all / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "valid_samples_S": st["S"], "neighbour_rows_M": st["M"], "rays_hit": st["rays_hit"],
+            "strong_scaling_4096_total": strong,
             "roofline": {"kernel": "forward + backward launchers (selection, query, field networks fwd + dgrad + wgrad on tcgen05, compositing)", "bound": "tensor", "achieved": ach, "peak": c.peaks["tensor"],
                          "unit": "TFLOP/s", "frac": ach / c.peaks["tensor"], "flops_per_step": flops, "ms_per_step": field_ms},
             "workload": "training step fwd+bwd+all-reduce+Adam (fields 5e-4, neural points 2e-3), 4096 rays per rank drawn from the "
