@@ -735,12 +735,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) field_tc_kern
 // ---------------------------------------------------------------------------------------------- colour network
 // mlp_color 280 -> 128 -> 128 -> 128 (LeakyReLU) + rgb head 128 -> 3 (sigmoid, *1.002 - 0.001), SM:355-359.
 // CTA pairs again (cta_group::2, M = 256 = 128 samples per CTA, N = 128): each CTA keeps only ITS 64 output features of the three
-// weight matrices resident (68 KB instead of 136 KB), which leaves room for TWO sample-tile slots per CTA.  Warps 0-7 / 8-15 own
-// slot 0 / 1 (thread = sample = TMEM lane, two threads per sample: 64 output columns each): the bf16 features of field_tc_kernel
-// arrive by bulk copy as the A operand [F_s 256 | PE(v) 24 | 0 x 8], then the three epilogues; warp 16 of the leader issues the
-// MMAs for whichever slot is ready (the weights are resident, so the order is free): one slot's gather and epilogues hide under the
-// other's MMAs.  v1 (one slot, 128 threads, everything serial per tile) ran at 12.6 % tensor-pipe activity, 18 k clk per tile;
-// v2 (two slots, one thread per sample) 7.8 k; v3 (this one) halves the epilogues' latency chains.
+// weight matrices resident (68 KB instead of 136 KB), which leaves room for TWO sample-tile slots per CTA.  Warps 0-3 / 4-7 own
+// slot 0 / 1 (thread = sample = TMEM lane): gather the bf16 features of field_tc_kernel into the A operand [F_s 256 | PE(v) 24 | 0 x 8],
+// then the three epilogues; warp 8 of the leader issues the MMAs for whichever slot is ready (the weights are resident, so the order
+// is free): one slot's gather and epilogues hide under the other's MMAs.  v1 (one slot, 128 threads, everything serial per tile) ran
+// at 12.6 % tensor-pipe activity, 18 k clk per tile.
 struct ColorParams {
     const uint8_t* F;              // 128-sample tiles of 32 k-slabs, written by field_tc_kernel
     const int* sample_ids;
@@ -763,11 +762,9 @@ struct SmemC {
     uint8_t W3[C2H_BYTES];
     float bias[3][HC];
     float w4[3][HC];
-    float rgb_hi[2][ROWS][3];       // rgb head: partial dots of columns 64..127 (upper-half warp -> lower-half warp)
     uint64_t bar_w, a_ready[2], acc_full[2], f_full[2];
     uint32_t tmem_base;
 };
-constexpr int CNT = 17 * 32;        // colour kernel: 2 slots x (4 lane quarters x 2 column halves) epilogue warps + the issuer warp
 static_assert(sizeof(SmemC) <= 232448, "color_tc_kernel shared memory exceeds the 227 KB per-CTA limit");
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   // non-blocking
@@ -783,7 +780,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {   //
 #define PNERF_COLOR_SPLIT 1
 #endif
 template <bool SAVE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CNT, 1) color_tc_kernel(const ColorParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(288, 1) color_tc_kernel(const ColorParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     SmemC& sm = *reinterpret_cast<SmemC*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -794,11 +791,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CNT, 1) color_tc_ker
     const int n_my = n_super > pair ? (n_super - pair + n_pairs - 1) / n_pairs : 0;
     if (tid == 0) {
         mbar_init(&sm.bar_w, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&sm.a_ready[s], 16); mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.f_full[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&sm.a_ready[s], 8); mbar_init(&sm.acc_full[s], 1); mbar_init(&sm.f_full[s], 1); }
         fence_barrier_init();
     }
-    if (warp == 16) tmem_alloc2(&sm.tmem_base, 256);
-    for (int i = tid; i < HC; i += CNT) {
+    if (warp == 8) tmem_alloc2(&sm.tmem_base, 256);
+    for (int i = tid; i < HC; i += 288) {
         sm.bias[0][i] = p.bc1[i]; sm.bias[1][i] = p.bc2[i]; sm.bias[2][i] = p.bc3[i];
         sm.w4[0][i] = p.wc4[i]; sm.w4[1][i] = p.wc4[HC + i]; sm.w4[2][i] = p.wc4[2 * HC + i];
     }
@@ -814,36 +811,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CNT, 1) color_tc_ker
         bulk_g2s(sm.W3, p.wpack_c + C1_BYTES + C2_BYTES + rank * C2H_BYTES, C2H_BYTES, &sm.bar_w);
     }
     constexpr int SJ = SLAB / 16;
-    if (warp < 16) {
-        // ===================================================== slot group: 8 warps = 4 TMEM lane quarters x 2 column halves; a thread
-        // owns one sample row (its TMEM lane) and 64 of the 128 output columns of every layer, so a layer's epilogue is two
-        // tcgen05.ld + 64 columns of math per thread instead of four + 128 (the epilogues are latency chains: v2 with one thread
-        // per row and all 128 columns took 7.8 k clk per tile)
-        const int s = warp >> 3, half = (warp >> 2) & 1, row = (warp & 3) * 32 + lane;
+    if (warp < 8) {
+        // ===================================================== slot group: thread = sample row
+        const int s = warp >> 2, row = tid & 127;
         const uint32_t tacc_lane = tmem + (uint32_t)(s * HC) + ((uint32_t)((warp & 3) * 32) << 16);
-        const int bar_id = 1 + s * 4 + (warp & 3);      // named barrier of the two warps that share a lane quarter
         uint4* Arow = reinterpret_cast<uint4*>(sm.A[s] + row * 16);
         uint32_t ph = 0, fph = 0;
         bool w_ready = false;
-        const bool fetcher = row == 0 && half == 0;
         // the F part of the A operand (slabs 0..31 = 64 KB, contiguous in global memory) arrives by bulk copy; the copy for the slot's
         // next tile is issued as soon as the last layer's MMAs have released the buffer
         auto tile_of = [&](int j) { return 2 * (pair + j * n_pairs) + (int)rank; };
         // in two halves: k-slabs 16..31 are free as soon as the tile's FIRST layer is done (layers 2 and 3 read slabs 0..15 only),
         // slabs 0..15 after its last layer; the first half only announces its bytes, the second one arrives
-        auto fetch = [&](int j, int hf) {
+        auto fetch = [&](int j, int half) {
             const int ct = tile_of(j);
             if (ct * ROWS >= S) return;
             constexpr uint32_t HB = (uint32_t)(F_TILE_BYTES / 2);
-            if (hf == 1) mbar_expect_tx(&sm.f_full[s], HB);
+            if (half == 1) mbar_expect_tx(&sm.f_full[s], HB);
             else mbar_arrive_expect_tx(&sm.f_full[s], HB);
 #pragma unroll
             for (int q = 0; q < 2; q++) {
-                const uint32_t off = (uint32_t)hf * HB + (uint32_t)q * (HB / 2);
+                const uint32_t off = (uint32_t)half * HB + (uint32_t)q * (HB / 2);
                 bulk_g2s(sm.A[s] + off, p.F + (int64_t)ct * F_TILE_BYTES + off, HB / 2, &sm.f_full[s]);
             }
         };
-        if (fetcher && s < n_my) { fetch(s, 1); fetch(s, 0); }
+        if (row == 0 && s < n_my) { fetch(s, 1); fetch(s, 0); }
         for (int j = s; j < n_my; j += 2) {
             const int ctile = tile_of(j);
             const int si = ctile * ROWS + row;
@@ -854,35 +846,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CNT, 1) color_tc_ker
                 slot = __ldg(p.sample_ids + si);
                 if (SAVE) {
 #pragma unroll 8
-                    for (int q = 16 * half; q < 16 * half + 16; q++) grow[q * SJ] = Arow[q * SJ];
+                    for (int q = 0; q < 32; q++) grow[q * SJ] = Arow[q * SJ];
                 }
-                if (half == 0) {
-                    const int ray = slot / p.SR;
-                    const float rd[3] = {__ldg(p.dirs + 3 * (int64_t)ray), __ldg(p.dirs + 3 * (int64_t)ray + 1), __ldg(p.dirs + 3 * (int64_t)ray + 2)};
-                    float v[3];
-                    rot_w2c(p.cam, rd, v);
-                    float t[32];              // ori=True layout minus the raw copy: [sin (d-major, f-minor) 12 | cos 12] (SM:305-306)
+                const int ray = slot / p.SR;
+                const float rd[3] = {__ldg(p.dirs + 3 * (int64_t)ray), __ldg(p.dirs + 3 * (int64_t)ray + 1), __ldg(p.dirs + 3 * (int64_t)ray + 2)};
+                float v[3];
+                rot_w2c(p.cam, rd, v);
+                float t[32];              // ori=True layout minus the raw copy: [sin (d-major, f-minor) 12 | cos 12] (SM:305-306)
 #pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        float q8[8];
-                        pe<4>(v[d], q8);
+                for (int d = 0; d < 3; d++) {
+                    float q8[8];
+                    pe<4>(v[d], q8);
 #pragma unroll
-                        for (int f = 0; f < 4; f++) { t[d * 4 + f] = q8[2 * f]; t[12 + d * 4 + f] = q8[2 * f + 1]; }
-                    }
+                    for (int f = 0; f < 4; f++) { t[d * 4 + f] = q8[2 * f]; t[12 + d * 4 + f] = q8[2 * f + 1]; }
+                }
 #pragma unroll
-                    for (int q = 24; q < 32; q++) t[q] = 0.f;
-                    t[24] = 1.f;      // column 280: multiplied by a zero weight here; the backward's weight-gradient GEMM reads it as the ones column of d bc1
+                for (int q = 24; q < 32; q++) t[q] = 0.f;
+                t[24] = 1.f;      // column 280: multiplied by a zero weight here; the backward's weight-gradient GEMM reads it as the ones column of d bc1
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const uint4 pv = pack8(t + 8 * q);
-                        Arow[(32 + q) * SJ] = pv;
-                        if (SAVE) grow[(32 + q) * SJ] = pv;
-                    }
+                for (int q = 0; q < 4; q++) {
+                    const uint4 pv = pack8(t + 8 * q);
+                    Arow[(32 + q) * SJ] = pv;
+                    if (SAVE) grow[(32 + q) * SJ] = pv;
                 }
             } else {
                 const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 6
-                for (int q = 18 * half; q < 18 * half + 18; q++) {
+#pragma unroll 4
+                for (int q = 0; q < 36; q++) {
                     Arow[q * SJ] = z;
                     if (SAVE) grow[q * SJ] = z;
                 }
@@ -896,7 +886,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CNT, 1) color_tc_ker
             for (int L = 0; L < 3; L++) {
                 mbar_wait(&sm.acc_full[s], ph); ph ^= 1;
                 tc_fence_after();
-                if (fetcher && j + 2 < n_my) {
+                if (row == 0 && j + 2 < n_my) {
                     if (PNERF_COLOR_SPLIT) {
                         if (L == 0) fetch(j + 2, 1);
                         if (L == 2) fetch(j + 2, 0);     // the tile's last MMAs are done with the A buffer
@@ -905,12 +895,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CNT, 1) color_tc_ker
                     }
                 }
                 float r[3] = {0.f, 0.f, 0.f};
-                float va[32], vb[32];
-                const int cb = half * (HC / 2);
-                tmem_ld32(tacc_lane + cb, va);
-                tmem_ld32(tacc_lane + cb + 32, vb);
-                tmem_ld_wait();
-                auto piece = [&](float (&v)[32], int c0) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < HC; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tacc_lane + c0, v);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 32; q++) {
                         const float x = v[q] + sm.bias[L][c0 + q];
@@ -931,23 +920,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CNT, 1) color_tc_ker
                             r[2] = fmaf(v[q], sm.w4[2][c0 + q], r[2]);
                         }
                     }
-                };
-                piece(va, cb);
-                piece(vb, cb + 32);
+                }
                 if (L < 2) {
                     fence_proxy_async();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(&sm.a_ready[s], 0);
-                } else {
-                    if (half) { sm.rgb_hi[s][row][0] = r[0]; sm.rgb_hi[s][row][1] = r[1]; sm.rgb_hi[s][row][2] = r[2]; }
-                    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-                    if (!half && slot >= 0) {
+                } else if (slot >= 0) {
 #pragma unroll
-                        for (int q = 0; q < 3; q++) {
-                            const float x = r[q] + sm.rgb_hi[s][row][q] + __ldg(p.bc4 + q);
-                            p.rgb[3 * (int64_t)slot + q] = (1.f / (1.f + __expf(-x))) * (1.f + 2.f * 0.001f) - 0.001f;   // SM:359
-                        }
+                    for (int q = 0; q < 3; q++) {
+                        const float x = r[q] + __ldg(p.bc4 + q);
+                        p.rgb[3 * (int64_t)slot + q] = (1.f / (1.f + __expf(-x))) * (1.f + 2.f * 0.001f) - 0.001f;   // SM:359
                     }
                 }
             }
@@ -984,7 +967,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CNT, 1) color_tc_ker
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 16) tmem_dealloc2(tmem, 256);
+    if (warp == 8) tmem_dealloc2(tmem, 256);
 }
 
 // ---------------------------------------------------------------------------------------------- weight packing
@@ -1121,10 +1104,10 @@ int field_tc_launch(const pnerf_points* pts, const pnerf_camera* cam, const pner
     const size_t csmem = sizeof(SmemC);
     if (csave) {
         PNERF_CUDA(cudaFuncSetAttribute(color_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-        color_tc_kernel<true><<<cgrid, CNT, csmem, st>>>(c);
+        color_tc_kernel<true><<<cgrid, 288, csmem, st>>>(c);
     } else {
         PNERF_CUDA(cudaFuncSetAttribute(color_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-        color_tc_kernel<false><<<cgrid, CNT, csmem, st>>>(c);
+        color_tc_kernel<false><<<cgrid, 288, csmem, st>>>(c);
     }
     PNERF_LAUNCH_CHECK();
 #ifdef PNERF_TC_TIMING
