@@ -336,6 +336,21 @@ __global__ void __launch_bounds__(128, KMAX <= 8 ? PNERF_Q_MINB : (KMAX == 16 ? 
                 if (!__any_sync(0xffffffffu, searching)) break;
             }
         }
+        // The insertion keeps exactly equal distances in visit order, which is what decides WHO is among the K nearest (CU:274-293:
+        // a later candidate replaces the farthest only if it is strictly closer).  The emitted order is the canonical (d2, point index)
+        // of the oracle: adjacent entries of the first K with equal d2 are put in ascending index -- one bubble pass, repeated only
+        // while some lane of the warp still swapped (ties are rare: coincident points).
+        for (;;) {
+            bool swapped = false;
+#pragma unroll
+            for (int i = 0; i + 1 < KMAX; i++) {
+                const bool sw = i + 1 < K && bd2[i] == bd2[i + 1] && bidx[i] > bidx[i + 1] && bidx[i + 1] >= 0;
+                const int a = bidx[i], b = bidx[i + 1];
+                bidx[i] = sw ? b : a; bidx[i + 1] = sw ? a : b;
+                swapped |= sw;
+            }
+            if (!__any_sync(0xffffffffu, swapped)) break;
+        }
         if (in_range) {
             int* out = sample_pidx + sid * K;
             if (K == KMAX && (KMAX % 4) == 0) {

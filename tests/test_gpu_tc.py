@@ -29,7 +29,7 @@ def _weights(flow):
 
 
 @pytest.mark.parametrize("name,flow", [("config1", "plugin"), ("config1", "original"), ("k16_5cube", "plugin"), ("tinyP", "plugin"),
-                                       ("scannet_like", "plugin")])
+                                       ("scannet_like", "plugin"), ("k24_5cube", "plugin")])
 def test_tc_forward_matches_fp32_oracle(name, flow):
     s, cloud, cam, pix = _scene(name)
     vs = s.get("vsize", 0.004)
