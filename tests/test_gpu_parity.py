@@ -63,6 +63,9 @@ SCENES = {
     "config1": dict(n=50000, radii=(0.11, 0.16, 0.2), SR=40, K=8, P=12, ks=(3, 3, 3), rays=1024),
     "k16_5cube": dict(n=20000, radii=(0.07, 0.1), SR=24, K=16, P=10, ks=(5, 5, 5), rays=600),
     "tinyP": dict(n=20000, radii=(0.05, 0.07), SR=16, K=4, P=3, ks=(3, 3, 3), rays=512),
+    # more points per voxel than the bucket holds (the cloud is thinned to 12 per voxel, the grid keeps P = 4): the deterministic
+    # rule "a voxel keeps its first P points in ascending index" (the reference keeps whichever P win its atomics race, CU:117-162)
+    "capP": dict(n=40000, radii=(0.06, 0.085), SR=24, K=8, P=4, cloud_P=12, ks=(3, 3, 3), rays=500),
     # K > 16: the 32-entry list of query_kernel<32> and the 32-rows-per-sample class of the field kernels
     "k24_5cube": dict(n=30000, radii=(0.07, 0.1), SR=16, K=24, P=10, ks=(5, 5, 5), rays=400),
     # BASELINE configs[3] geometry (dev_scripts/w_scannet_etf/scene101_points.sh:24-37): vsize 0.008 x vscale 2, radius 0.032, P = 30, SR = 24
@@ -77,7 +80,7 @@ TIE_SCENE = dict(n=30000, radii=(0.07, 0.1), SR=16, K=8, P=12, ks=(3, 3, 3), ray
 def _scene(name):
     from pointnerf2studio_b200.synth import make_camera, make_cloud
     s = TIE_SCENE if name == "dups" else SCENES[name]
-    cloud = make_cloud(s["n"], seed=1234 + len(name), radii=s["radii"], P=s["P"], scaled_vsize=2 * s.get("vsize", 0.004),
+    cloud = make_cloud(s["n"], seed=1234 + len(name), radii=s["radii"], P=s.get("cloud_P", s["P"]), scaled_vsize=2 * s.get("vsize", 0.004),
                        kernel_size=s["ks"])
     if s.get("dups"):
         rd = np.random.default_rng(77)
@@ -119,6 +122,10 @@ def test_grid_select_query_bit_exact(name):
     bits = grid.occ_bits.cpu().numpy().view(np.uint32)
     occ = ((bits[:, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1)[:frame.cells].astype(bool)
     np.testing.assert_array_equal(occ, og.occ.reshape(-1))
+    if "cloud_P" in s:       # the cap did fire: some voxel holds more points than its bucket
+        lin = ((cloud.xyz - frame_o.lo) / frame_o.sv).astype(np.int64)
+        key = (lin[:, 0] * frame_o.dim[1] + lin[:, 1]) * frame_o.dim[2] + lin[:, 2]
+        assert np.bincount(np.unique(key, return_inverse=True)[1]).max() > s["P"] == cnt.max()
     # three position sources give the same samples
     R = len(pix)
     for src in ("raypos", "t_shared"):
