@@ -49,8 +49,8 @@ def _bundle(cam, pix):
                      metadata={"camrotc2w": _cuda(cam.R_c2w)})
 
 
-def _oracle_query(cloud_xyz, cam, pix, SR, K, P, ks, D=400, jitter=0.0, vsize=0.004):
-    frame = gq.hyperparameters(cloud_xyz, [vsize] * 3, [2, 2, 2], list(ks), RANGES)
+def _oracle_query(cloud_xyz, cam, pix, SR, K, P, ks, D=400, jitter=0.0, vsize=0.004, ranges=None):
+    frame = gq.hyperparameters(cloud_xyz, [vsize] * 3, [2, 2, 2], list(ks), ranges or RANGES)
     raypos, t_mid = of.coarse_positions(torch.from_numpy(cam.origin), torch.from_numpy(cam.rays(pix)), D, cam.near, cam.far,
                                         jitter=jitter, generator=torch.Generator().manual_seed(3))
     radius = np.float32(4 * vsize)                       # SU:110
@@ -66,6 +66,9 @@ SCENES = {
     # more points per voxel than the bucket holds (the cloud is thinned to 12 per voxel, the grid keeps P = 4): the deterministic
     # rule "a voxel keeps its first P points in ascending index" (the reference keeps whichever P win its atomics race, CU:117-162)
     "capP": dict(n=40000, radii=(0.06, 0.085), SR=24, K=8, P=4, cloud_P=12, ks=(3, 3, 3), rays=500),
+    # `ranges` cut through the cloud (SU:115-121): points outside the box never enter the grid, and the 3x3x3 neighbourhoods of the
+    # samples next to its faces are clipped at the grid's edge
+    "clipped": dict(n=40000, radii=(0.08, 0.11), SR=24, K=8, P=12, ks=(3, 3, 3), rays=600, ranges=[-0.06, -0.05, -0.07, 0.05, 0.06, 0.04]),
     # K > 16: the 32-entry list of query_kernel<32> and the 32-rows-per-sample class of the field kernels
     "k24_5cube": dict(n=30000, radii=(0.07, 0.1), SR=16, K=24, P=10, ks=(5, 5, 5), rays=400),
     # BASELINE configs[3] geometry (dev_scripts/w_scannet_etf/scene101_points.sh:24-37): vsize 0.008 x vscale 2, radius 0.032, P = 30, SR = 24
@@ -102,10 +105,11 @@ def test_grid_select_query_bit_exact(name):
     from pointnerf2studio_b200 import native
     s, cloud, cam, pix = _scene(name)
     vs = s.get("vsize", 0.004)
+    ranges = s.get("ranges", RANGES)
     frame_o, raypos, t_mid, pidx_o, loc_o, mask_o, hit_o, stats_o = _oracle_query(cloud.xyz, cam, pix, s["SR"], s["K"], s["P"], s["ks"],
-                                                                                 vsize=vs)
+                                                                                 vsize=vs, ranges=ranges)
     xyz = _cuda(cloud.xyz)
-    frame = native.get_hyperparameters(xyz, [vs] * 3, [2, 2, 2], list(s["ks"]), RANGES)
+    frame = native.get_hyperparameters(xyz, [vs] * 3, [2, 2, 2], list(s["ks"]), ranges)
     np.testing.assert_array_equal(frame.lo, frame_o.lo)
     np.testing.assert_array_equal(frame.dim, frame_o.dim)
     grid = native.VoxelGrid(xyz, frame, s["P"], [3, 3, 3])
